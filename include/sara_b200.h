@@ -1,0 +1,221 @@
+/* ========================================================================== *
+ * sara_b200.h -- C ABI of the B200-native SIFT path.
+ *
+ * Drop-in boundary for ONE path of oddkiva/sara: per-frame SIFT
+ *   Gaussian pyramid -> DoG -> scale-space extrema (+refinement, edge
+ *   rejection) -> dominant orientations -> 128-D descriptors.
+ * The reference has no FFI for this path; its boundary is the C++ signature
+ *   DO::Sara::compute_sift_keypoints      cpp/src/DO/Sara/FeatureDetectors/SIFT.hpp:24-33
+ * (bound to Python at python/oddkiva/sara/pybind11/FeatureDetectors.cpp:116-124)
+ * and the stage functor
+ *   DO::Sara::ComputeDoGExtrema           cpp/src/DO/Sara/FeatureDetectors/DoG.hpp:72-165.
+ * Every entry point below names the reference interface it replaces.  Plain
+ * pointers and sizes only; nothing here throws; all functions return 0 on
+ * success or a negative sara_b200_status and leave a message retrievable with
+ * sara_b200_last_error().
+ *
+ * Threading contract: one ctx per (host thread, GPU).  Calls on one ctx are
+ * serialised by the caller; different ctxs are independent.  A ctx owns
+ * `num_slots` independent frame slots (device arena + stream each) so that
+ * several frames can be in flight: enqueue on slot i, collect slot i later.
+ *
+ * There is NO CPU fallback: if no CUDA device is usable sara_b200_create fails
+ * with SARA_B200_ERR_CUDA.
+ * ========================================================================== */
+#ifndef SARA_B200_H
+#define SARA_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#  define SARA_B200_API __attribute__((visibility("default")))
+#else
+#  define SARA_B200_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SARA_B200_VERSION 100 /* 0.1.0 */
+
+typedef enum sara_b200_status
+{
+  SARA_B200_OK = 0,
+  SARA_B200_ERR_BAD_ARG = -1,         /* std::domain_error / std::range_error in the reference */
+  SARA_B200_ERR_TOO_FEW_SCALES = -2,  /* std::runtime_error, DoG.hpp:86-89 */
+  SARA_B200_ERR_CUDA = -3,            /* SHAKTI_SAFE_CUDA_CALL would throw */
+  SARA_B200_ERR_OOM = -4,
+  SARA_B200_ERR_OVERFLOW = -5,        /* more keypoints than the ctx / caller buffers hold */
+  SARA_B200_ERR_BUSY = -6             /* slot has an un-collected frame */
+} sara_b200_status;
+
+/* ImagePyramidParams, cpp/src/DO/Sara/ImageProcessing/ImagePyramid.hpp:33-49
+ * (same fields, same order, same defaults via sara_b200_default_pyramid_params). */
+typedef struct sara_b200_pyramid_params
+{
+  int32_t first_octave_index;     /* -1 */
+  int32_t scale_count_per_octave; /* 3 + 3 */
+  float scale_geometric_factor;   /* 2^(1/3) */
+  int32_t image_padding_size;     /* 1 */
+  float scale_camera;             /* 0.5 */
+  float scale_initial;            /* 1.6 */
+  int32_t num_octaves_max;        /* INT_MAX */
+} sara_b200_pyramid_params;
+
+/* One keypoint.  The first 34 bytes carry the fields of DO::Sara::OERegion
+ * (cpp/src/DO/Sara/Features/Feature.hpp:40-179) in declaration order; (s, o)
+ * is the entry of `scale_octave_pairs` (DoG.cpp:70-82); (xi, yi) is the raster
+ * slot of the DoG layer the extremum was emitted at (RefineExtremum.cpp:495-515). */
+typedef struct sara_b200_keypoint
+{
+  float x, y;            /* OERegion::coords */
+  float shape[4];        /* OERegion::shape_matrix, column-major (= I / sigma^2) */
+  float orientation;     /* OERegion::orientation */
+  float extremum_value;  /* OERegion::extremum_value */
+  uint8_t type;          /* OERegion::Type, stays Undefined (= 11) as in the reference */
+  int8_t extremum_type;  /* OERegion::ExtremumType: -1 Min, 1 Max */
+  int16_t reserved;
+  int32_t s, o;
+  int32_t xi, yi;
+} sara_b200_keypoint; /* 52 bytes */
+
+typedef struct sara_b200_ctx sara_b200_ctx;
+
+/* Limits a ctx is sized for; everything is allocated once at creation. */
+typedef struct sara_b200_limits
+{
+  int32_t max_width;       /* of the INPUT image */
+  int32_t max_height;
+  int32_t max_keypoints;   /* per frame, <= 0 -> 262144 */
+  int32_t num_slots;       /* frames in flight, <= 0 -> 1 */
+  int32_t min_first_octave_index; /* most negative first_octave_index to size for (0 or -1) */
+} sara_b200_limits;
+
+/* SIFT arguments: exactly the scalar arguments of compute_sift_keypoints
+ * (SIFT.hpp:26-32).  `parallel` has no meaning on the GPU and is omitted. */
+typedef struct sara_b200_sift_args
+{
+  sara_b200_pyramid_params pyramid_params;
+  float gauss_truncate;             /* 4.f  */
+  float extremum_thres;             /* 0.01f */
+  float edge_ratio_thres;           /* 10.f */
+  int32_t extremum_refinement_iter; /* 5; NB SIFT.cpp:45-51 passes it as img_padding_sz */
+} sara_b200_sift_args;
+
+/* Arguments of the ComputeDoGExtrema constructor, DoG.hpp:72-78. */
+typedef struct sara_b200_dog_args
+{
+  sara_b200_pyramid_params pyramid_params;
+  float gauss_truncate;
+  float extremum_thres;
+  float edge_ratio_thres;
+  int32_t img_padding_sz;
+  int32_t extremum_refinement_iter;
+} sara_b200_dog_args;
+
+/* Stage timings of the last frame run with profiling on, in ms (CUDA events). */
+typedef struct sara_b200_timings
+{
+  float upload;      /* host -> device copy of the frame */
+  float pyramid;     /* Gaussian pyramid + DoG (all octaves) */
+  float extrema;     /* classify + compaction + refinement */
+  float orientation; /* dominant orientations + expansion */
+  float descriptor;  /* 128-D descriptors */
+  float total;       /* first kernel to last kernel */
+  int32_t pyramid_launches; /* kernels launched by the pyramid stage */
+  int32_t total_launches;   /* kernels launched for the frame */
+} sara_b200_timings;
+
+SARA_B200_API int sara_b200_version(void);
+SARA_B200_API const char* sara_b200_last_error(const sara_b200_ctx* ctx); /* ctx may be NULL: creation errors */
+
+SARA_B200_API void sara_b200_default_pyramid_params(sara_b200_pyramid_params* p); /* ImagePyramid.hpp:36-42 */
+SARA_B200_API void sara_b200_default_sift_args(sara_b200_sift_args* a);           /* SIFT.hpp:26-32 */
+SARA_B200_API void sara_b200_default_dog_args(sara_b200_dog_args* a);             /* DoG.hpp:72-78 */
+
+SARA_B200_API int sara_b200_create(int device, const sara_b200_limits* limits, sara_b200_ctx** out);
+SARA_B200_API void sara_b200_destroy(sara_b200_ctx* ctx);
+
+/* Pinned host memory helpers (frames and results move at PCIe speed only from
+ * pinned memory). */
+SARA_B200_API int sara_b200_host_alloc(void** ptr, uint64_t bytes);
+SARA_B200_API void sara_b200_host_free(void* ptr);
+
+/* Record CUDA events around the stages (sara_b200_last_timings). */
+SARA_B200_API int sara_b200_set_profiling(sara_b200_ctx* ctx, int on);
+SARA_B200_API int sara_b200_last_timings(sara_b200_ctx* ctx, int slot, sara_b200_timings* out);
+
+/* ---- compute_sift_keypoints (SIFT.hpp:24-33) ------------------------------
+ * Synchronous form: image in (host pointer, or device pointer when
+ * `image_on_device`), keypoints + descriptors out into caller-owned HOST
+ * buffers of `capacity` entries (descriptors: capacity x 128 floats, row-major,
+ * as Tensor_<float, 2>, KeypointList.hpp:35-36).  *n_out receives the number of
+ * keypoints; if it exceeds `capacity` nothing is copied and OVERFLOW is
+ * returned with *n_out set, so a caller can retry with larger buffers via
+ * sara_b200_collect.  image: w x h float32, contiguous, x fastest
+ * (ImageView<float>, Core/Image/Image.hpp:44-103). */
+SARA_B200_API int sara_b200_sift(sara_b200_ctx* ctx, const float* image, int w, int h, int image_on_device,
+                   const sara_b200_sift_args* args, sara_b200_keypoint* keypoints,
+                   float* descriptors, int capacity, int* n_out);
+
+/* Asynchronous form: enqueue the whole frame on `slot`'s stream (or on
+ * `stream`, a cudaStream_t passed as void*, when non-NULL) and return at once;
+ * collect later.  A host `image` must stay valid until the matching collect. */
+SARA_B200_API int sara_b200_sift_enqueue(sara_b200_ctx* ctx, int slot, const float* image, int w, int h,
+                           int image_on_device, const sara_b200_sift_args* args, void* stream);
+/* Waits for the slot, copies results to host buffers (either may be NULL to
+ * skip that copy), frees the slot. */
+SARA_B200_API int sara_b200_collect(sara_b200_ctx* ctx, int slot, sara_b200_keypoint* keypoints,
+                      float* descriptors, int capacity, int* n_out);
+/* Device-resident results of a finished slot (for GPU consumers such as a
+ * matcher): pointers stay valid until the slot is enqueued again. */
+SARA_B200_API int sara_b200_device_results(sara_b200_ctx* ctx, int slot, const sara_b200_keypoint** keypoints,
+                             const float** descriptors, int* n_out);
+/* Waits for the slot's GPU work and reads back only the keypoint count. */
+SARA_B200_API int sara_b200_wait(sara_b200_ctx* ctx, int slot, int* n_out);
+
+/* ---- ComputeDoGExtrema::operator() (DoG.hpp:116-131, DoG.cpp:23-87) --------
+ * Pyramid + DoG + extrema only, explicit padding / iteration arguments.
+ * Results stay in the slot; read them with the accessors below. */
+SARA_B200_API int sara_b200_dog_extrema(sara_b200_ctx* ctx, int slot, const float* image, int w, int h,
+                          int image_on_device, const sara_b200_dog_args* args);
+
+/* ---- gaussian_pyramid + difference_of_gaussians_pyramid only --------------
+ * (GaussianPyramid.hpp:35-125, GaussianPyramid.cpp:23-51): the "fused pyramid
+ * + DoG" benchmark configuration.  Asynchronous on the slot's stream (or
+ * `stream`); finish with sara_b200_wait. */
+SARA_B200_API int sara_b200_pyramid_enqueue(sara_b200_ctx* ctx, int slot, const float* image, int w, int h,
+                              int image_on_device, const sara_b200_pyramid_params* params,
+                              float gauss_truncate, void* stream);
+
+/* ---- stage accessors: ComputeDoGExtrema::gaussians(), diff_of_gaussians(),
+ * extrema(s, o) (DoG.hpp:133-165) -------------------------------------------- */
+SARA_B200_API int sara_b200_num_octaves(sara_b200_ctx* ctx, int slot);
+SARA_B200_API int sara_b200_num_scales(sara_b200_ctx* ctx, int slot);  /* Gaussian layers per octave */
+SARA_B200_API int sara_b200_layer_size(sara_b200_ctx* ctx, int slot, int octave, int* w, int* h);
+SARA_B200_API float sara_b200_octave_scaling_factor(sara_b200_ctx* ctx, int slot, int octave);
+/* which: 0 = Gaussian G(s, o), 1 = DoG D(s, o).  dst: w*h floats on the host. */
+SARA_B200_API int sara_b200_copy_layer(sara_b200_ctx* ctx, int slot, int which, int s, int o, float* dst);
+/* Extrema before orientation assignment, octave coordinates, reference order
+ * (octave-major, scale-minor, raster). */
+SARA_B200_API int sara_b200_copy_extrema(sara_b200_ctx* ctx, int slot, sara_b200_keypoint* dst, int capacity,
+                           int* n_out);
+/* Oriented keypoints in octave coordinates (before the rescale of SIFT.cpp:92-98). */
+SARA_B200_API int sara_b200_copy_oriented(sara_b200_ctx* ctx, int slot, sara_b200_keypoint* dst, int capacity,
+                            int* n_out);
+
+/* ---- building blocks exposed for unit parity (same semantics as the
+ * reference functions named) --------------------------------------------------
+ * gaussian(): LinearFiltering.hpp:446-454 / LinearFiltering.cpp:30-68;
+ * host in, host out. */
+SARA_B200_API int sara_b200_gaussian(sara_b200_ctx* ctx, const float* src, int w, int h, float sigma,
+                       float gauss_truncate, float* dst);
+/* make_gaussian_kernel(): LinearFiltering.hpp:172-203.  Returns the tap count
+ * (negative of the needed capacity if `capacity` is too small). */
+SARA_B200_API int sara_b200_make_gaussian_kernel(float sigma, float gauss_truncate, float* taps, int capacity);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SARA_B200_H */

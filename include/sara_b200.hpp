@@ -1,0 +1,328 @@
+// ========================================================================== //
+// sara_b200.hpp -- header-only C++17 adapter over the C ABI (sara_b200.h).
+//
+// Keeps the C++ surface of the reference path so that a Sara call site switches
+// by changing a namespace:
+//
+//   DO::Sara::compute_sift_keypoints(image, pyramid_params, gauss_truncate,
+//       extremum_thres, edge_ratio_thres, extremum_refinement_iter, parallel)
+//       -> KeypointList<OERegion, float>        FeatureDetectors/SIFT.hpp:24-33
+//
+// Without Eigen/Sara headers on the include path the types below are Eigen-free
+// POD mirrors with the same member names and memory order:
+//   ImageView<float>      Core/Image/Image.hpp:44-103   (data(), width(), height())
+//   ImagePyramidParams    ImageProcessing/ImagePyramid.hpp:29-198
+//   OERegion              Features/Feature.hpp:40-179
+//   KeypointList<F, T>    Features/KeypointList.hpp:35-36  = tuple<vector<F>, Tensor_<T, 2>>
+// With <DO/Sara/Features/KeypointList.hpp> reachable (a real Sara build), define
+// SARA_B200_WITH_SARA before including this header and the overload taking and
+// returning the REAL Sara types is compiled as well.
+//
+// Errors: the C ABI never throws; this adapter rethrows the std exception the
+// reference would have thrown (std::runtime_error for < 4 scales, DoG.hpp:86-89;
+// std::domain_error for bad sizes, LinearFiltering.hpp:82-84).
+// ========================================================================== //
+#pragma once
+
+#include <cmath>
+#include <cstdint>
+#include <limits>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+#include <utility>
+#include <vector>
+
+#include "sara_b200.h"
+
+namespace sara_b200 {
+
+  // ---- ImageView<float> ---------------------------------------------------- //
+  template <typename T>
+  class ImageView;
+
+  template <>
+  class ImageView<float>
+  {
+  public:
+    ImageView() = default;
+    ImageView(const float* data, int width, int height)
+      : _data{data}
+      , _w{width}
+      , _h{height}
+    {
+    }
+    const float* data() const { return _data; }
+    int width() const { return _w; }
+    int height() const { return _h; }
+    float operator()(int x, int y) const { return _data[static_cast<std::size_t>(y) * _w + x]; }
+
+  private:
+    const float* _data = nullptr;
+    int _w = 0, _h = 0;
+  };
+
+  // ---- ImagePyramidParams ---------------------------------------------------- //
+  class ImagePyramidParams
+  {
+  public:
+    ImagePyramidParams(int first_octave_index = -1, int scale_count_per_octave = 3 + 3,
+                       float scale_geometric_factor = std::pow(2.f, 1.f / 3.f),
+                       int image_padding_size = 1, float scale_camera = 0.5f,
+                       float scale_initial = 1.6f,
+                       int num_octaves_max = std::numeric_limits<int>::max())
+      : _p{first_octave_index, scale_count_per_octave, scale_geometric_factor, image_padding_size,
+           scale_camera, scale_initial, num_octaves_max}
+    {
+    }
+    int first_octave_index() const { return _p.first_octave_index; }
+    int scale_count_per_octave() const { return _p.scale_count_per_octave; }
+    float scale_geometric_factor() const { return _p.scale_geometric_factor; }
+    int image_padding_size() const { return _p.image_padding_size; }
+    float scale_camera() const { return _p.scale_camera; }
+    float scale_initial() const { return _p.scale_initial; }
+    int num_octaves_max() const { return _p.num_octaves_max; }
+    const sara_b200_pyramid_params& c_params() const { return _p; }
+
+  private:
+    sara_b200_pyramid_params _p;
+  };
+
+  // ---- OERegion (POD mirror: same member names, same order) ---------------- //
+  struct Point2f
+  {
+    float v[2] = {0.f, 0.f};
+    float operator()(int i) const { return v[i]; }
+    float& operator()(int i) { return v[i]; }
+    float x() const { return v[0]; }
+    float y() const { return v[1]; }
+  };
+
+  struct Matrix2f  // column-major like Eigen's default
+  {
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    float operator()(int r, int c) const { return v[c * 2 + r]; }
+    float& operator()(int r, int c) { return v[c * 2 + r]; }
+  };
+
+  struct OERegion
+  {
+    enum class Type : std::uint8_t
+    {
+      Harris, HarAff, HarLap, FAST, SUSAN, DoG, LoG, DoH, MSER, HesAff, HesLap, Undefined
+    };
+    enum class ExtremumType : std::int8_t
+    {
+      Min = -1, Saddle = 0, Max = 1, Undefined = -2
+    };
+
+    float x() const { return coords(0); }
+    float y() const { return coords(1); }
+    const Point2f& center() const { return coords; }
+    // Feature.cpp:28-39 for the isotropic shape matrices this path produces.
+    float radius(float = 0.f) const { return 1.f / std::sqrt(shape_matrix(0, 0)); }
+    float scale(float a = 0.f) const { return radius(a); }
+
+    Point2f coords;
+    Matrix2f shape_matrix;
+    float orientation = 0.f;
+    float extremum_value = 0.f;
+    Type type = Type::Undefined;
+    ExtremumType extremum_type = ExtremumType::Undefined;
+  };
+
+  // ---- Tensor_<float, 2> (row-major N x 128) -------------------------------- //
+  class DescriptorMatrix
+  {
+  public:
+    DescriptorMatrix() = default;
+    DescriptorMatrix(int rows, int cols)
+      : _rows{rows}
+      , _cols{cols}
+      , _data(static_cast<std::size_t>(rows) * cols)
+    {
+    }
+    int rows() const { return _rows; }
+    int cols() const { return _cols; }
+    int size(int i) const { return i == 0 ? _rows : _cols; }
+    float* data() { return _data.data(); }
+    const float* data() const { return _data.data(); }
+    const float* operator[](int r) const { return _data.data() + static_cast<std::size_t>(r) * _cols; }
+    float operator()(int r, int c) const { return (*this)[r][c]; }
+
+  private:
+    int _rows = 0, _cols = 0;
+    std::vector<float> _data;
+  };
+
+  template <typename F, typename T>
+  using KeypointList = std::tuple<std::vector<F>, DescriptorMatrix>;
+
+  template <typename F, typename T>
+  inline const std::vector<F>& features(const KeypointList<F, T>& keys)
+  {
+    return std::get<0>(keys);
+  }
+  template <typename F, typename T>
+  inline const DescriptorMatrix& descriptors(const KeypointList<F, T>& keys)
+  {
+    return std::get<1>(keys);
+  }
+
+  // ---- error mapping ---------------------------------------------------------- //
+  [[noreturn]] inline void rethrow(int rc, const sara_b200_ctx* ctx)
+  {
+    const std::string msg = sara_b200_last_error(ctx);
+    switch (rc)
+    {
+    case SARA_B200_ERR_BAD_ARG:
+      throw std::domain_error{msg};
+    case SARA_B200_ERR_OVERFLOW:
+      throw std::length_error{msg};
+    case SARA_B200_ERR_OOM:
+      throw std::bad_alloc{};
+    default:
+      throw std::runtime_error{msg};  // TOO_FEW_SCALES (DoG.hpp:86-89), CUDA, BUSY
+    }
+  }
+
+  // ---- RAII context ------------------------------------------------------------ //
+  class Context
+  {
+  public:
+    Context(int max_width, int max_height, int device = 0, int max_keypoints = 262144,
+            int num_slots = 1, int min_first_octave_index = -1)
+    {
+      sara_b200_limits lim{max_width, max_height, max_keypoints, num_slots, min_first_octave_index};
+      sara_b200_ctx* c = nullptr;
+      const int rc = sara_b200_create(device, &lim, &c);
+      if (rc != 0)
+        rethrow(rc, nullptr);
+      _ctx.reset(c);
+      _max_w = max_width;
+      _max_h = max_height;
+      _max_kp = max_keypoints;
+    }
+    sara_b200_ctx* get() const { return _ctx.get(); }
+    bool fits(int w, int h) const { return w <= _max_w && h <= _max_h; }
+
+    // The drop-in body of compute_sift_keypoints, filling any keypoint type whose
+    // members are named like OERegion's.
+    template <typename Region, typename MakeDescriptors>
+    auto compute(const float* image, int w, int h, const sara_b200_sift_args& args,
+                 MakeDescriptors&& make_descriptors)
+    {
+      int rc = sara_b200_sift_enqueue(get(), 0, image, w, h, 0, &args, nullptr);
+      if (rc != 0)
+        rethrow(rc, get());
+      int n = 0;
+      rc = sara_b200_wait(get(), 0, &n);
+      if (rc != 0)
+        rethrow(rc, get());
+      std::vector<sara_b200_keypoint> raw(static_cast<std::size_t>(n > 0 ? n : 1));
+      auto desc = make_descriptors(n, 128);
+      rc = sara_b200_collect(get(), 0, raw.data(), desc.data(), n > 0 ? n : 1, &n);
+      if (rc != 0)
+        rethrow(rc, get());
+      std::vector<Region> regions(static_cast<std::size_t>(n));
+      for (int i = 0; i < n; ++i)
+      {
+        const sara_b200_keypoint& k = raw[i];
+        Region& r = regions[i];
+        r.coords(0) = k.x;
+        r.coords(1) = k.y;
+        r.shape_matrix(0, 0) = k.shape[0];
+        r.shape_matrix(1, 0) = k.shape[1];
+        r.shape_matrix(0, 1) = k.shape[2];
+        r.shape_matrix(1, 1) = k.shape[3];
+        r.orientation = k.orientation;
+        r.extremum_value = k.extremum_value;
+        r.type = static_cast<decltype(r.type)>(k.type);
+        r.extremum_type = static_cast<decltype(r.extremum_type)>(k.extremum_type);
+      }
+      return std::make_tuple(std::move(regions), std::move(desc));
+    }
+
+  private:
+    struct Deleter
+    {
+      void operator()(sara_b200_ctx* c) const { sara_b200_destroy(c); }
+    };
+    std::unique_ptr<sara_b200_ctx, Deleter> _ctx;
+    int _max_w = 0, _max_h = 0, _max_kp = 0;
+  };
+
+  // Per-thread default context (the reference function is stateless; one ctx per
+  // host thread keeps that contract, see the threading note in sara_b200.h).
+  inline Context& default_context(int w, int h)
+  {
+    thread_local std::unique_ptr<Context> ctx;
+    if (!ctx || !ctx->fits(w, h))
+      ctx = std::make_unique<Context>(w, h);
+    return *ctx;
+  }
+
+  inline sara_b200_sift_args make_sift_args(const sara_b200_pyramid_params& pp, float gauss_truncate,
+                                            float extremum_thres, float edge_ratio_thres,
+                                            int extremum_refinement_iter)
+  {
+    sara_b200_sift_args a;
+    a.pyramid_params = pp;
+    a.gauss_truncate = gauss_truncate;
+    a.extremum_thres = extremum_thres;
+    a.edge_ratio_thres = edge_ratio_thres;
+    a.extremum_refinement_iter = extremum_refinement_iter;
+    return a;
+  }
+
+  //! Same signature and defaults as DO::Sara::compute_sift_keypoints
+  //! (FeatureDetectors/SIFT.hpp:24-33).  `parallel` is accepted for source
+  //! compatibility; the GPU path is always parallel.
+  inline auto compute_sift_keypoints(const ImageView<float>& image,
+                                     const ImagePyramidParams& pyramid_params = ImagePyramidParams(),
+                                     float gauss_truncate = 4.f, float extremum_thres = 0.01f,
+                                     float edge_ratio_thres = 10.f, int extremum_refinement_iter = 5,
+                                     bool /*parallel*/ = false) -> KeypointList<OERegion, float>
+  {
+    const auto args = make_sift_args(pyramid_params.c_params(), gauss_truncate, extremum_thres,
+                                     edge_ratio_thres, extremum_refinement_iter);
+    return default_context(image.width(), image.height())
+        .compute<OERegion>(image.data(), image.width(), image.height(), args,
+                           [](int n, int d) { return DescriptorMatrix{n, d}; });
+  }
+
+}  // namespace sara_b200
+
+
+// ---- real Sara types (compiled only inside a Sara build) --------------------- //
+#if defined(SARA_B200_WITH_SARA)
+#  include <DO/Sara/Core/Image.hpp>
+#  include <DO/Sara/Features/KeypointList.hpp>
+#  include <DO/Sara/ImageProcessing/ImagePyramid.hpp>
+
+namespace sara_b200 {
+
+  // Expected layout of DO::Sara::OERegion with default Eigen alignment.
+  static_assert(sizeof(DO::Sara::OERegion) == 48, "unexpected OERegion layout");
+
+  inline auto compute_sift_keypoints(const DO::Sara::ImageView<float>& image,
+                                     const DO::Sara::ImagePyramidParams& pp = DO::Sara::ImagePyramidParams(),
+                                     float gauss_truncate = 4.f, float extremum_thres = 0.01f,
+                                     float edge_ratio_thres = 10.f, int extremum_refinement_iter = 5,
+                                     bool /*parallel*/ = false)
+      -> DO::Sara::KeypointList<DO::Sara::OERegion, float>
+  {
+    const sara_b200_pyramid_params cp{pp.first_octave_index(), pp.scale_count_per_octave(),
+                                      pp.scale_geometric_factor(), pp.image_padding_size(),
+                                      pp.scale_camera(), pp.scale_initial(), pp.num_octaves_max()};
+    const auto args =
+        make_sift_args(cp, gauss_truncate, extremum_thres, edge_ratio_thres, extremum_refinement_iter);
+    return default_context(image.width(), image.height())
+        .compute<DO::Sara::OERegion>(image.data(), image.width(), image.height(), args, [](int n, int d) {
+          return DO::Sara::Tensor_<float, 2>{n, d};
+        });
+  }
+
+}  // namespace sara_b200
+#endif

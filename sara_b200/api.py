@@ -1,0 +1,432 @@
+"""ctypes binding of include/sara_b200.h and the pysara-shaped host API.
+
+Reference interfaces mirrored here (paths relative to /root/reference):
+  * pysara.ImagePyramidParams        python/oddkiva/sara/pybind11/FeatureDetectors.cpp:70-88
+  * pysara.compute_sift_keypoints    python/oddkiva/sara/pybind11/FeatureDetectors.cpp:116-124
+  * pysara.features / descriptors    python/oddkiva/sara/pybind11/FeatureDetectors.cpp:57-68
+  * DO::Sara::ComputeDoGExtrema      cpp/src/DO/Sara/FeatureDetectors/DoG.hpp:72-165
+Error behaviour follows the reference: bad sizes raise ValueError
+(std::domain_error / std::range_error), fewer than 4 scales raises RuntimeError
+(DoG.hpp:86-89).  This module never touches oracle/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+KEYPOINT_DTYPE = np.dtype(
+    [
+        ("x", "<f4"), ("y", "<f4"), ("shape", "<f4", (4,)), ("orientation", "<f4"),
+        ("extremum_value", "<f4"), ("type", "u1"), ("extremum_type", "i1"), ("reserved", "<i2"),
+        ("s", "<i4"), ("o", "<i4"), ("xi", "<i4"), ("yi", "<i4"),
+    ]
+)
+assert KEYPOINT_DTYPE.itemsize == 52
+
+
+class SaraB200Error(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"sara_b200 error {code}: {msg}")
+        self.code = code
+
+
+class _PyrParams(C.Structure):
+    _fields_ = [
+        ("first_octave_index", C.c_int32), ("scale_count_per_octave", C.c_int32),
+        ("scale_geometric_factor", C.c_float), ("image_padding_size", C.c_int32),
+        ("scale_camera", C.c_float), ("scale_initial", C.c_float), ("num_octaves_max", C.c_int32),
+    ]
+
+
+class _Limits(C.Structure):
+    _fields_ = [
+        ("max_width", C.c_int32), ("max_height", C.c_int32), ("max_keypoints", C.c_int32),
+        ("num_slots", C.c_int32), ("min_first_octave_index", C.c_int32),
+    ]
+
+
+class _SiftArgs(C.Structure):
+    _fields_ = [
+        ("pyramid_params", _PyrParams), ("gauss_truncate", C.c_float), ("extremum_thres", C.c_float),
+        ("edge_ratio_thres", C.c_float), ("extremum_refinement_iter", C.c_int32),
+    ]
+
+
+class _DogArgs(C.Structure):
+    _fields_ = [
+        ("pyramid_params", _PyrParams), ("gauss_truncate", C.c_float), ("extremum_thres", C.c_float),
+        ("edge_ratio_thres", C.c_float), ("img_padding_sz", C.c_int32),
+        ("extremum_refinement_iter", C.c_int32),
+    ]
+
+
+class Timings(C.Structure):
+    _fields_ = [
+        ("upload", C.c_float), ("pyramid", C.c_float), ("extrema", C.c_float),
+        ("orientation", C.c_float), ("descriptor", C.c_float), ("total", C.c_float),
+        ("pyramid_launches", C.c_int32), ("total_launches", C.c_int32),
+    ]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+# Every symbol include/sara_b200.h declares (tests check the library exports all).
+SYMBOLS = [
+    "sara_b200_version", "sara_b200_last_error", "sara_b200_default_pyramid_params",
+    "sara_b200_default_sift_args", "sara_b200_default_dog_args", "sara_b200_create",
+    "sara_b200_destroy", "sara_b200_host_alloc", "sara_b200_host_free", "sara_b200_set_profiling",
+    "sara_b200_last_timings", "sara_b200_sift", "sara_b200_sift_enqueue", "sara_b200_collect",
+    "sara_b200_device_results", "sara_b200_wait", "sara_b200_dog_extrema",
+    "sara_b200_pyramid_enqueue", "sara_b200_num_octaves", "sara_b200_num_scales",
+    "sara_b200_layer_size", "sara_b200_octave_scaling_factor", "sara_b200_copy_layer",
+    "sara_b200_copy_extrema", "sara_b200_copy_oriented", "sara_b200_gaussian",
+    "sara_b200_make_gaussian_kernel",
+]
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, "libsara_b200.so")
+
+
+def load_library() -> C.CDLL:
+    """Loads (building first when the sources are newer) the C-ABI library.
+
+    Fails loudly when it is missing: there is no other implementation."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    from . import build as _build
+
+    path = _build.build()
+    if not os.path.exists(path):
+        raise ImportError(f"{path} is missing: build it with `python -m sara_b200.build`")
+    L = C.CDLL(path)
+    vp, ip, fp = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float)
+    L.sara_b200_last_error.restype = C.c_char_p
+    L.sara_b200_last_error.argtypes = [vp]
+    L.sara_b200_create.argtypes = [C.c_int, C.POINTER(_Limits), C.POINTER(vp)]
+    L.sara_b200_destroy.argtypes = [vp]
+    L.sara_b200_destroy.restype = None
+    L.sara_b200_host_alloc.argtypes = [C.POINTER(vp), C.c_uint64]
+    L.sara_b200_host_free.argtypes = [vp]
+    L.sara_b200_host_free.restype = None
+    L.sara_b200_set_profiling.argtypes = [vp, C.c_int]
+    L.sara_b200_last_timings.argtypes = [vp, C.c_int, C.POINTER(Timings)]
+    L.sara_b200_sift.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(_SiftArgs), vp, vp, C.c_int, ip]
+    L.sara_b200_sift_enqueue.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.POINTER(_SiftArgs), vp]
+    L.sara_b200_collect.argtypes = [vp, C.c_int, vp, vp, C.c_int, ip]
+    L.sara_b200_device_results.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), ip]
+    L.sara_b200_wait.argtypes = [vp, C.c_int, ip]
+    L.sara_b200_dog_extrema.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.POINTER(_DogArgs)]
+    L.sara_b200_pyramid_enqueue.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.POINTER(_PyrParams), C.c_float, vp]
+    L.sara_b200_num_octaves.argtypes = [vp, C.c_int]
+    L.sara_b200_num_scales.argtypes = [vp, C.c_int]
+    L.sara_b200_layer_size.argtypes = [vp, C.c_int, C.c_int, ip, ip]
+    L.sara_b200_octave_scaling_factor.argtypes = [vp, C.c_int, C.c_int]
+    L.sara_b200_octave_scaling_factor.restype = C.c_float
+    L.sara_b200_copy_layer.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+    L.sara_b200_copy_extrema.argtypes = [vp, C.c_int, vp, C.c_int, ip]
+    L.sara_b200_copy_oriented.argtypes = [vp, C.c_int, vp, C.c_int, ip]
+    L.sara_b200_gaussian.argtypes = [vp, vp, C.c_int, C.c_int, C.c_float, C.c_float, vp]
+    L.sara_b200_make_gaussian_kernel.argtypes = [C.c_float, C.c_float, fp, C.c_int]
+    L.sara_b200_default_pyramid_params.argtypes = [C.POINTER(_PyrParams)]
+    L.sara_b200_default_sift_args.argtypes = [C.POINTER(_SiftArgs)]
+    L.sara_b200_default_dog_args.argtypes = [C.POINTER(_DogArgs)]
+    _LIB = L
+    return L
+
+
+@dataclass
+class ImagePyramidParams:
+    """ImagePyramidParams (cpp/src/DO/Sara/ImageProcessing/ImagePyramid.hpp:33-49).
+
+    Defaults are the C++ ones (first_octave_index = -1); the pybind11 wrapper
+    defaults first_octave_index to 1 (FeatureDetectors.cpp:72), callers of the
+    SfM path pass 0 (SfM/BuildingBlocks/FeatureParams.hpp:10)."""
+
+    first_octave_index: int = -1
+    scale_count_per_octave: int = 6
+    scale_geometric_factor: float = float(np.float32(2.0) ** np.float32(1.0 / 3.0))
+    image_padding_size: int = 1
+    scale_camera: float = 0.5
+    scale_initial: float = 1.6
+    num_octaves_max: int = 2**31 - 1
+
+    def _c(self) -> _PyrParams:
+        return _PyrParams(
+            int(self.first_octave_index), int(self.scale_count_per_octave),
+            float(self.scale_geometric_factor), int(self.image_padding_size),
+            float(self.scale_camera), float(self.scale_initial), int(self.num_octaves_max))
+
+
+class KeypointList:
+    """KeypointList<OERegion, float> = (features, descriptors)
+    (cpp/src/DO/Sara/Features/KeypointList.hpp:35-36)."""
+
+    def __init__(self, feats: np.ndarray, descs: np.ndarray):
+        self.features = feats
+        self.descriptors = descs
+
+    def __len__(self):
+        return len(self.features)
+
+
+def features(kl: KeypointList) -> np.ndarray:
+    return kl.features
+
+
+def descriptors(kl: KeypointList) -> np.ndarray:
+    return kl.descriptors
+
+
+def _raise(L, ctx, rc: int):
+    msg = L.sara_b200_last_error(ctx).decode(errors="replace")
+    if rc == -1:
+        raise ValueError(msg)  # std::domain_error / range_error
+    if rc == -2:
+        raise RuntimeError(msg)  # DoG.hpp:86-89
+    raise SaraB200Error(rc, msg)
+
+
+def _as_image(image):
+    """Returns (pointer, w, h, on_device, keepalive)."""
+    if hasattr(image, "data_ptr"):  # torch tensor
+        t = image
+        if t.dim() != 2 or str(t.dtype) != "torch.float32" or not t.is_contiguous():
+            raise ValueError("image tensor must be 2-D contiguous float32")
+        return t.data_ptr(), int(t.shape[1]), int(t.shape[0]), bool(t.is_cuda), t
+    a = np.ascontiguousarray(image, dtype=np.float32)
+    if a.ndim != 2:
+        raise ValueError("image must be HxW float32")
+    return a.ctypes.data, int(a.shape[1]), int(a.shape[0]), False, a
+
+
+class SiftContext:
+    """One GPU context (see the threading contract in include/sara_b200.h)."""
+
+    def __init__(self, max_width: int, max_height: int, device: int = 0, max_keypoints: int = 262144,
+                 num_slots: int = 1, min_first_octave_index: int = -1):
+        self._L = load_library()
+        self._ctx = C.c_void_p()
+        lim = _Limits(max_width, max_height, max_keypoints, num_slots, min_first_octave_index)
+        rc = self._L.sara_b200_create(device, C.byref(lim), C.byref(self._ctx))
+        if rc != 0:
+            _raise(self._L, None, rc)
+        self.max_keypoints = max_keypoints
+        self.num_slots = num_slots
+        self._keep = {}
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._L.sara_b200_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            _raise(self._L, self._ctx, rc)
+
+    # ---- compute_sift_keypoints ------------------------------------------------
+    @staticmethod
+    def _sift_args(pp, gauss_truncate, extremum_thres, edge_ratio_thres, extremum_refinement_iter):
+        return _SiftArgs((pp or ImagePyramidParams())._c(), gauss_truncate, extremum_thres,
+                         edge_ratio_thres, int(extremum_refinement_iter))
+
+    def set_profiling(self, on: bool):
+        self._check(self._L.sara_b200_set_profiling(self._ctx, int(on)))
+
+    def timings(self, slot: int = 0) -> dict:
+        t = Timings()
+        self._check(self._L.sara_b200_last_timings(self._ctx, slot, C.byref(t)))
+        return t.asdict()
+
+    def enqueue(self, slot, image, pyramid_params=None, gauss_truncate=4.0, extremum_thres=0.01,
+                edge_ratio_thres=10.0, extremum_refinement_iter=5, stream=None):
+        ptr, w, h, on_dev, keep = _as_image(image)
+        args = self._sift_args(pyramid_params, gauss_truncate, extremum_thres, edge_ratio_thres,
+                               extremum_refinement_iter)
+        self._keep[slot] = keep
+        self._check(self._L.sara_b200_sift_enqueue(self._ctx, slot, ptr, w, h, int(on_dev), C.byref(args),
+                                                   C.c_void_p(stream) if stream else None))
+
+    def enqueue_raw(self, slot, ptr, w, h, on_device, args, stream=None):
+        self._check(self._L.sara_b200_sift_enqueue(self._ctx, slot, ptr, w, h, int(on_device), C.byref(args),
+                                                   C.c_void_p(stream) if stream else None))
+
+    def wait(self, slot=0) -> int:
+        n = C.c_int()
+        self._check(self._L.sara_b200_wait(self._ctx, slot, C.byref(n)))
+        return n.value
+
+    def collect(self, slot=0, out_keypoints=None, out_descriptors=None) -> KeypointList:
+        n = self.wait(slot)
+        self._keep.pop(slot, None)
+        kps = out_keypoints if out_keypoints is not None else np.empty(max(n, 1), KEYPOINT_DTYPE)
+        desc = out_descriptors if out_descriptors is not None else np.empty((max(n, 1), 128), np.float32)
+        m = C.c_int()
+        self._check(self._L.sara_b200_collect(self._ctx, slot, kps.ctypes.data, desc.ctypes.data,
+                                              len(kps), C.byref(m)))
+        return KeypointList(kps[: m.value], desc[: m.value])
+
+    def collect_into(self, slot, kps_ptr, desc_ptr, capacity) -> int:
+        m = C.c_int()
+        self._check(self._L.sara_b200_collect(self._ctx, slot, kps_ptr, desc_ptr, capacity, C.byref(m)))
+        return m.value
+
+    def compute_sift_keypoints(self, image, pyramid_params=None, gauss_truncate=4.0, extremum_thres=0.01,
+                               edge_ratio_thres=10.0, extremum_refinement_iter=5, parallel=True) -> KeypointList:
+        self.enqueue(0, image, pyramid_params, gauss_truncate, extremum_thres, edge_ratio_thres,
+                     extremum_refinement_iter)
+        return self.collect(0)
+
+    # ---- pyramid only ---------------------------------------------------------------
+    def pyramid_enqueue(self, slot, image, pyramid_params=None, gauss_truncate=4.0, stream=None):
+        ptr, w, h, on_dev, keep = _as_image(image)
+        pp = (pyramid_params or ImagePyramidParams())._c()
+        self._keep[slot] = keep
+        self._check(self._L.sara_b200_pyramid_enqueue(self._ctx, slot, ptr, w, h, int(on_dev), C.byref(pp),
+                                                      gauss_truncate, C.c_void_p(stream) if stream else None))
+
+    # ---- ComputeDoGExtrema ------------------------------------------------------------
+    def dog_extrema(self, image, pyramid_params=None, gauss_truncate=4.0, extremum_thres=0.01,
+                    edge_ratio_thres=10.0, img_padding_sz=1, extremum_refinement_iter=5, slot=0) -> np.ndarray:
+        ptr, w, h, on_dev, keep = _as_image(image)
+        args = _DogArgs((pyramid_params or ImagePyramidParams())._c(), gauss_truncate, extremum_thres,
+                        edge_ratio_thres, int(img_padding_sz), int(extremum_refinement_iter))
+        self._check(self._L.sara_b200_dog_extrema(self._ctx, slot, ptr, w, h, int(on_dev), C.byref(args)))
+        del keep
+        return self.extrema(slot)
+
+    # ---- stage accessors -----------------------------------------------------------------
+    def num_octaves(self, slot=0) -> int:
+        return self._L.sara_b200_num_octaves(self._ctx, slot)
+
+    def num_scales(self, slot=0) -> int:
+        return self._L.sara_b200_num_scales(self._ctx, slot)
+
+    def layer_size(self, o, slot=0):
+        w, h = C.c_int(), C.c_int()
+        self._check(self._L.sara_b200_layer_size(self._ctx, slot, o, C.byref(w), C.byref(h)))
+        return w.value, h.value
+
+    def octave_scaling_factor(self, o, slot=0) -> float:
+        return float(self._L.sara_b200_octave_scaling_factor(self._ctx, slot, o))
+
+    def _layer(self, which, s, o, slot):
+        w, h = self.layer_size(o, slot)
+        a = np.empty((h, w), np.float32)
+        self._check(self._L.sara_b200_copy_layer(self._ctx, slot, which, s, o, a.ctypes.data))
+        return a
+
+    def gaussian_layer(self, s, o, slot=0) -> np.ndarray:
+        return self._layer(0, s, o, slot)
+
+    def dog_layer(self, s, o, slot=0) -> np.ndarray:
+        return self._layer(1, s, o, slot)
+
+    def _kps(self, fn, slot):
+        n = C.c_int()
+        rc = fn(self._ctx, slot, None, 0, C.byref(n))
+        if n.value == 0:
+            if rc not in (0, -5):
+                self._check(rc)
+            return np.empty(0, KEYPOINT_DTYPE)
+        a = np.empty(n.value, KEYPOINT_DTYPE)
+        self._check(fn(self._ctx, slot, a.ctypes.data, len(a), C.byref(n)))
+        return a
+
+    def extrema(self, slot=0) -> np.ndarray:
+        return self._kps(self._L.sara_b200_copy_extrema, slot)
+
+    def oriented(self, slot=0) -> np.ndarray:
+        return self._kps(self._L.sara_b200_copy_oriented, slot)
+
+    def device_results(self, slot=0):
+        kp, ds, n = C.c_void_p(), C.c_void_p(), C.c_int()
+        self._check(self._L.sara_b200_device_results(self._ctx, slot, C.byref(kp), C.byref(ds), C.byref(n)))
+        return kp.value, ds.value, n.value
+
+    # ---- building blocks -------------------------------------------------------------------
+    def gaussian(self, image, sigma: float, gauss_truncate: float = 4.0) -> np.ndarray:
+        a = np.ascontiguousarray(image, dtype=np.float32)
+        out = np.empty_like(a)
+        self._check(self._L.sara_b200_gaussian(self._ctx, a.ctypes.data, a.shape[1], a.shape[0], sigma,
+                                               gauss_truncate, out.ctypes.data))
+        return out
+
+
+def make_gaussian_kernel(sigma: float, gauss_truncate: float = 4.0) -> np.ndarray:
+    L = load_library()
+    buf = np.zeros(256, np.float32)
+    n = L.sara_b200_make_gaussian_kernel(sigma, gauss_truncate, buf.ctypes.data_as(C.POINTER(C.c_float)), 256)
+    if n < 0:
+        raise ValueError(f"kernel needs {-n} taps")
+    return buf[:n].copy()
+
+
+class ComputeDoGExtrema:
+    """DO::Sara::ComputeDoGExtrema (FeatureDetectors/DoG.hpp:72-165): same constructor
+    arguments, call operator and accessors."""
+
+    def __init__(self, pyramid_params: ImagePyramidParams | None = None, gauss_truncate=4.0,
+                 extremum_thres=0.01, edge_ratio_thres=10.0, img_padding_sz=1, extremum_refinement_iter=5,
+                 device: int = 0):
+        self.params = pyramid_params or ImagePyramidParams()
+        if self.params.scale_count_per_octave < 4:
+            raise RuntimeError("Error: The extraction of DoG extrema needs (1 + 3) = 4 scales per octave "
+                               "at the very minimum!")
+        self.args = (gauss_truncate, extremum_thres, edge_ratio_thres, img_padding_sz, extremum_refinement_iter)
+        self.device = device
+        self._ctx = None
+
+    def __call__(self, image):
+        """Returns (extrema, scale_octave_pairs) as DoG.cpp:23-87."""
+        _, w, h, _, _ = _as_image(image)
+        if self._ctx is None:
+            self._ctx = SiftContext(w, h, self.device, min_first_octave_index=min(self.params.first_octave_index, 0))
+        e = self._ctx.dog_extrema(image, self.params, *self.args)
+        return e, np.stack([e["s"], e["o"]], axis=1)
+
+    def gaussians(self, s, o):
+        return self._ctx.gaussian_layer(s, o)
+
+    def diff_of_gaussians(self, s, o):
+        return self._ctx.dog_layer(s, o)
+
+    def extrema(self, s, o):
+        e = self._ctx.extrema()
+        return e[(e["s"] == s) & (e["o"] == o)]
+
+
+_DEFAULT_CTX: dict = {}
+
+
+def compute_sift_keypoints(image, pyramid_params: ImagePyramidParams | None = None, gauss_truncate: float = 4.0,
+                           extremum_thres: float = 0.01, edge_ratio_thres: float = 10.0,
+                           extremum_refinement_iter: int = 5, parallel: bool = True, device: int = 0) -> KeypointList:
+    """pysara.compute_sift_keypoints (pybind11/FeatureDetectors.cpp:116-124), same
+    argument order and defaults; `parallel` is accepted and ignored (the GPU path is
+    always parallel)."""
+    _, w, h, _, _ = _as_image(image)
+    key = device
+    ctx = _DEFAULT_CTX.get(key)
+    if ctx is None or ctx._w < w or ctx._h < h:
+        if ctx is not None:
+            ctx.close()
+        ctx = SiftContext(w, h, device)
+        ctx._w, ctx._h = w, h
+        _DEFAULT_CTX[key] = ctx
+    return ctx.compute_sift_keypoints(image, pyramid_params, gauss_truncate, extremum_thres, edge_ratio_thres,
+                                      extremum_refinement_iter)

@@ -1,0 +1,100 @@
+// Shared declarations of the B200-native SIFT path (device descriptors, limits,
+// error helpers).  Product code: never includes or links anything from oracle/.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/sara_b200.h"
+
+namespace sb {
+
+  constexpr int kMaxOctaves = 16;
+  constexpr int kMaxScales = 12;  // Gaussian layers per octave
+  constexpr int kMaxTaps = 129;   // generic separable filter: radius <= 64
+  constexpr int kMaxOri = 18;     // strict local maxima of a 36-bin ring
+
+  // One octave of the pyramid in HBM.  All layers of an octave share (w, h,
+  // pitch); Gaussian layer s is G + s * layer_stride, DoG layer s is
+  // D + s * layer_stride (floats).  pitch is a multiple of 32 floats so that
+  // every row starts on a 128-byte line (TMA needs 16-byte row strides).
+  struct OctaveDesc
+  {
+    float* G;
+    float* D;
+    uint8_t* map;   // extremum map, (n_scales - 3) layers of w * h bytes (ImageProcessing/Extrema.hpp)
+    int* row_count; // (n_scales - 3) * h ints: candidates per raster row
+    int w, h, pitch;
+    int layer_stride;
+    int seg_base;   // index of this octave's first row segment in the global segment list
+    float scaling;  // ImagePyramid::octave_scaling_factor(o)
+  };
+
+  struct PyramidDesc
+  {
+    int n_octaves;
+    int n_scales;               // Gaussian layers per octave
+    float scale_rel[kMaxScales];  // float(scale_relative_to_octave(s)), ImagePyramid.hpp:316-319
+    float k;                    // scale_geometric_factor
+    OctaveDesc oct[kMaxOctaves];
+  };
+
+  struct Taps
+  {
+    int n;
+    float v[kMaxTaps];
+  };
+
+  // Candidate extremum produced by the classify + compaction passes.
+  struct Candidate
+  {
+    int x, y;
+    int so;    // (o << 8) | s
+    int type;  // uint8 map value: 1 for maxima, 255 for minima (reference quirk N2)
+  };
+
+  // Device-side counters of one frame slot.
+  struct Counters
+  {
+    int n_cand;
+    int n_ext;
+    int n_kp;
+    int overflow;  // bit 0: candidates, bit 1: extrema, bit 2: keypoints
+  };
+
+  typedef sara_b200_keypoint Keypoint;
+  static_assert(sizeof(Keypoint) == 52, "keypoint record layout is part of the ABI");
+
+  // ---- kernel launchers (defined in the .cu files) --------------------------
+  void launch_gaussian_stage(const float* src, int src_pitch, float* dst, int dst_pitch,
+                             float* dog, int dog_pitch, int w, int h, const Taps& taps,
+                             cudaStream_t st);
+  void launch_downscale(const float* src, int sw, int sh, int spitch, float* dst, int dw, int dh,
+                        int dpitch, cudaStream_t st);
+  void launch_enlarge(const float* src, int sw, int sh, int spitch, float* dst, int dw, int dh,
+                      int dpitch, cudaStream_t st);
+  void launch_copy2d(const float* src, int spitch, float* dst, int dpitch, int w, int h,
+                     cudaStream_t st);
+
+  // Fused octave kernel for the default SIFT schedule (pyramid_fused.cu).
+  bool fused_octave_supported(const Taps* taps, int n_scales);
+  void launch_fused_octave(const OctaveDesc& oct, const OctaveDesc* next, int downscale_index,
+                           const Taps* taps, int n_scales, cudaStream_t st);
+
+  struct ExtremaParams
+  {
+    float extremum_thres;
+    float edge_ratio;
+    int pad;
+    int refine_iter;
+  };
+  int launch_extrema(const PyramidDesc& P, const ExtremaParams& ep, int n_segments, int* seg_offsets,
+                     Candidate* cand, int cap_cand, Keypoint* ext_tmp, uint8_t* keep, int* bsums,
+                     Keypoint* ext, int cap_ext, Counters* counters, cudaStream_t st);
+  int launch_orientation(const PyramidDesc& P, const Keypoint* ext, int cap_ext, int* ori_count,
+                         float* oris, int* bsums, Keypoint* kp_oct, int cap_kp, Counters* counters,
+                         cudaStream_t st);
+  int launch_descriptors(const PyramidDesc& P, const Keypoint* kp_oct, Keypoint* kp_out, float* desc,
+                         int cap_kp, Counters* counters, cudaStream_t st);
+
+}  // namespace sb

@@ -1,0 +1,991 @@
+// Host side of the C ABI (include/sara_b200.h): context, frame slots, pyramid
+// geometry, launch sequence.  No CPU compute path exists here: every stage is a
+// CUDA kernel launch, and creation fails when no device is usable.
+//
+// Host-side restatements (scalars only): ImagePyramidParams / gaussian_pyramid
+// orchestration (ImageProcessing/GaussianPyramid.hpp:35-125), make_gaussian_kernel
+// (ImageProcessing/LinearFiltering.hpp:172-203), ImagePyramid::scale_relative_to_octave
+// (ImageProcessing/ImagePyramid.hpp:316-319), the argument plumbing of
+// compute_sift_keypoints (FeatureDetectors/SIFT.cpp:27-108, quirk N1) and of
+// ComputeDoGExtrema (FeatureDetectors/DoG.cpp:23-87).
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+using namespace sb;
+
+namespace {
+
+  thread_local char g_create_error[512] = "";
+
+  struct Slot
+  {
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;  // stream of the frame in flight
+    // pyramid arena (grown on demand)
+    char* arena = nullptr;
+    size_t arena_bytes = 0;
+    // keypoint buffers (sized at creation)
+    char* kbuf = nullptr;
+    Candidate* cand = nullptr;
+    Keypoint* ext_tmp = nullptr;
+    Keypoint* ext = nullptr;
+    Keypoint* kp_oct = nullptr;
+    Keypoint* kp_out = nullptr;
+    float* desc = nullptr;
+    int* ori_count = nullptr;
+    float* oris = nullptr;
+    int* scratch = nullptr;
+    Counters* counters = nullptr;
+    Counters* h_counters = nullptr;  // pinned
+    // geometry of the frame in flight / last frame
+    PyramidDesc P{};
+    float* d_img = nullptr;
+    float* d_tmp = nullptr;
+    int* seg_offsets = nullptr;
+    int n_segments = 0;
+    int img_w = 0, img_h = 0;
+    int downscale_index = 0;
+    std::vector<Taps> stage_taps;  // per scale s >= 1
+    bool busy = false;
+    bool has_keypoints = false;  // the last frame ran the keypoint stages
+    cudaEvent_t ev[7] = {};
+    sara_b200_timings timings{};
+    int pyramid_launches = 0, total_launches = 0;
+  };
+
+  }  // namespace
+
+struct sara_b200_ctx
+{
+  int device = 0;
+  sara_b200_limits lim{};
+  int cap_kp = 0, cap_ext = 0, cap_cand = 0;
+  bool profiling = false;
+  std::vector<Slot> slots;
+  char err[512] = "";
+};
+
+namespace {
+
+  int fail(sara_b200_ctx* ctx, int code, const char* fmt, ...)
+  {
+    char* dst = ctx ? ctx->err : g_create_error;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(dst, 512, fmt, ap);
+    va_end(ap);
+    return code;
+  }
+
+#define CU(ctx, call)                                                                              \
+  do                                                                                               \
+  {                                                                                                \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(ctx, e_ == cudaErrorMemoryAllocation ? SARA_B200_ERR_OOM : SARA_B200_ERR_CUDA,  \
+                  "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);     \
+  } while (0)
+
+  size_t align_up(size_t v, size_t a)
+  {
+    return (v + a - 1) / a * a;
+  }
+
+  // make_gaussian_kernel, LinearFiltering.hpp:172-203 (expf + sequential sum; the
+  // taps are computed once on the host and handed to the kernels as bits).
+  int make_taps(float sigma, float gauss_truncate, Taps* out)
+  {
+    int kernel_size = static_cast<int>(2 * gauss_truncate * sigma + 1);
+    kernel_size = std::max(3, kernel_size);
+    if (kernel_size % 2 == 0)
+      ++kernel_size;
+    if (kernel_size > kMaxTaps)
+      return -kernel_size;
+    const int c = kernel_size / 2;
+    const float denom = 2 * (sigma * sigma);
+    for (int i = 0; i < kernel_size; ++i)
+    {
+      const float d = static_cast<float>(i) - static_cast<float>(c);
+      out->v[i] = expf(-(d * d) / denom);
+    }
+    float sum = 0.f;
+    for (int i = 0; i < kernel_size; ++i)
+      sum += out->v[i];
+    for (int i = 0; i < kernel_size; ++i)
+      out->v[i] /= sum;
+    out->n = kernel_size;
+    return kernel_size;
+  }
+
+  struct Geometry
+  {
+    int base_w = 0, base_h = 0;
+    int n_octaves = 0, n_scales = 0, downscale_index = 0;
+    int ow[kMaxOctaves], oh[kMaxOctaves];
+    float scaling[kMaxOctaves];
+    float resize_factor = 1.f;
+    float pre_sigma = 0.f;  // > 0: pre-blur of the input image
+    int pre_downscale = 0;  // > 0: first_octave_index > 0
+  };
+
+  // gaussian_pyramid(), GaussianPyramid.hpp:35-125: sizes, octave count, scaling.
+  int plan_geometry(sara_b200_ctx* ctx, int w, int h, const sara_b200_pyramid_params& pp, Geometry* g)
+  {
+    if (w <= 0 || h <= 0)
+      return fail(ctx, SARA_B200_ERR_BAD_ARG, "image sizes must be positive (got %dx%d)", w, h);
+    if (pp.scale_count_per_octave < 1 || pp.scale_count_per_octave > kMaxScales)
+      return fail(ctx, SARA_B200_ERR_BAD_ARG, "scale_count_per_octave must be in [1, %d]", kMaxScales);
+    if (!(pp.scale_geometric_factor > 1.f))
+      return fail(ctx, SARA_B200_ERR_BAD_ARG, "scale_geometric_factor must be > 1");
+    if (pp.image_padding_size < 1)
+      return fail(ctx, SARA_B200_ERR_BAD_ARG, "image_padding_size must be >= 1");
+    if (pp.first_octave_index < -3 || pp.first_octave_index > 6)
+      return fail(ctx, SARA_B200_ERR_BAD_ARG, "first_octave_index out of the supported range [-3, 6]");
+
+    const float resize_factor = std::pow(2.f, -static_cast<float>(pp.first_octave_index));
+    const float camera_sigma = pp.scale_camera * resize_factor;
+    const float init_sigma = pp.scale_initial;
+    g->resize_factor = resize_factor;
+    g->pre_sigma = 0.f;
+    g->pre_downscale = 0;
+    if (pp.first_octave_index < 0)
+    {
+      // enlarge(image, fact): Resize.hpp:190-216, no blur at all (quirk N4).
+      const double fact = resize_factor;
+      g->base_w = static_cast<int>(static_cast<double>(w) * fact);
+      g->base_h = static_cast<int>(static_cast<double>(h) * fact);
+    }
+    else
+    {
+      if (camera_sigma < init_sigma)
+        g->pre_sigma = std::sqrt(init_sigma * init_sigma - camera_sigma * camera_sigma);
+      g->base_w = w;
+      g->base_h = h;
+      if (pp.first_octave_index > 0)
+      {
+        g->pre_downscale = static_cast<int>(std::round(1 / resize_factor));
+        g->base_w = w / g->pre_downscale;
+        g->base_h = h / g->pre_downscale;
+        if (g->base_w <= 0 || g->base_h <= 0)
+          return fail(ctx, SARA_B200_ERR_BAD_ARG, "image too small for first_octave_index %d",
+                      pp.first_octave_index);
+      }
+    }
+    const int l = std::min(g->base_w, g->base_h);
+    const int b = pp.image_padding_size;
+    int n_oct = std::min(static_cast<int>(logf(l / (2.f * b)) / logf(2.f)), pp.num_octaves_max);
+    n_oct = std::max(n_oct, 0);
+    if (n_oct > kMaxOctaves)
+      return fail(ctx, SARA_B200_ERR_BAD_ARG, "more than %d octaves", kMaxOctaves);
+    g->n_octaves = n_oct;
+    g->n_scales = pp.scale_count_per_octave;
+    g->downscale_index = static_cast<int>(floorf(logf(2.f) / logf(pp.scale_geometric_factor)));
+    if (n_oct > 1 && (g->downscale_index < 0 || g->downscale_index >= g->n_scales))
+      return fail(ctx, SARA_B200_ERR_BAD_ARG,
+                  "downscale index %d is outside the %d scales of an octave (GaussianPyramid.hpp:99-114)",
+                  g->downscale_index, g->n_scales);
+    int cw = g->base_w, ch = g->base_h;
+    for (int o = 0; o < n_oct; ++o)
+    {
+      if (o > 0)
+      {
+        cw /= 2;
+        ch /= 2;
+      }
+      if (cw <= 0 || ch <= 0)
+      {
+        g->n_octaves = o;
+        break;
+      }
+      g->ow[o] = cw;
+      g->oh[o] = ch;
+      g->scaling[o] = o == 0 ? 1 / resize_factor : g->scaling[o - 1] * 2;
+    }
+    return 0;
+  }
+
+  // Lays the pyramid, extremum maps and row counters out in the slot's arena.
+  int layout_slot(sara_b200_ctx* ctx, Slot& S, int w, int h, const Geometry& g,
+                  const sara_b200_pyramid_params& pp, bool image_on_device)
+  {
+    const int n_s = g.n_scales;
+    const int n_ext_layers = std::max(n_s - 3, 0);
+    size_t bytes = 0;
+    auto take = [&](size_t n) {
+      const size_t off = bytes;
+      bytes = align_up(bytes + n, 256);
+      return off;
+    };
+    const size_t off_img = image_on_device ? 0 : take(sizeof(float) * w * h);
+    const size_t off_tmp = g.pre_downscale > 0 ? take(sizeof(float) * w * h) : 0;
+    size_t off_G[kMaxOctaves], off_D[kMaxOctaves], off_map[kMaxOctaves];
+    int pitch[kMaxOctaves];
+    int n_seg = 0;
+    for (int o = 0; o < g.n_octaves; ++o)
+    {
+      pitch[o] = static_cast<int>(align_up(g.ow[o], 32));
+      const size_t layer = sizeof(float) * pitch[o] * g.oh[o];
+      off_G[o] = take(layer * n_s);
+      off_D[o] = take(layer * std::max(n_s - 1, 1));
+      off_map[o] = take(static_cast<size_t>(g.ow[o]) * g.oh[o] * std::max(n_ext_layers, 1));
+      n_seg += n_ext_layers * g.oh[o];
+    }
+    const size_t off_rows = take(sizeof(int) * std::max(n_seg, 1));
+    const size_t off_segoff = take(sizeof(int) * std::max(n_seg, 1));
+
+    if (bytes > S.arena_bytes)
+    {
+      if (S.arena)
+      {
+        CU(ctx, cudaStreamSynchronize(S.stream ? S.stream : S.own_stream));
+        CU(ctx, cudaFree(S.arena));
+        S.arena = nullptr;
+        S.arena_bytes = 0;
+      }
+      CU(ctx, cudaMalloc(&S.arena, bytes));
+      S.arena_bytes = bytes;
+    }
+    S.d_img = image_on_device ? nullptr : reinterpret_cast<float*>(S.arena + off_img);
+    S.d_tmp = g.pre_downscale > 0 ? reinterpret_cast<float*>(S.arena + off_tmp) : nullptr;
+    S.seg_offsets = reinterpret_cast<int*>(S.arena + off_segoff);
+    S.n_segments = n_seg;
+    S.img_w = w;
+    S.img_h = h;
+    S.downscale_index = g.downscale_index;
+
+    PyramidDesc& P = S.P;
+    std::memset(&P, 0, sizeof(P));
+    P.n_octaves = g.n_octaves;
+    P.n_scales = n_s;
+    P.k = pp.scale_geometric_factor;
+    for (int s = 0; s < n_s; ++s)  // ImagePyramid.hpp:316-319: pow(float, int) * float is a double
+      P.scale_rel[s] = static_cast<float>(std::pow(static_cast<double>(pp.scale_geometric_factor),
+                                                   static_cast<double>(s)) *
+                                          static_cast<double>(pp.scale_initial));
+    int seg_base = 0;
+    for (int o = 0; o < g.n_octaves; ++o)
+    {
+      OctaveDesc& oc = P.oct[o];
+      oc.G = reinterpret_cast<float*>(S.arena + off_G[o]);
+      oc.D = reinterpret_cast<float*>(S.arena + off_D[o]);
+      oc.map = reinterpret_cast<uint8_t*>(S.arena + off_map[o]);
+      oc.row_count = reinterpret_cast<int*>(S.arena + off_rows) + seg_base;
+      oc.w = g.ow[o];
+      oc.h = g.oh[o];
+      oc.pitch = pitch[o];
+      oc.layer_stride = pitch[o] * g.oh[o];
+      oc.seg_base = seg_base;
+      oc.scaling = g.scaling[o];
+      seg_base += n_ext_layers * g.oh[o];
+    }
+
+    // Per-scale increments, GaussianPyramid.hpp:116-121 (default truncate 4, quirk N5).
+    S.stage_taps.assign(n_s, Taps{});
+    const float k = pp.scale_geometric_factor;
+    float sigma_s_1 = pp.scale_initial;
+    for (int s = 1; s < n_s; ++s)
+    {
+      const float ks = k * sigma_s_1;
+      const float sigma = sqrtf(ks * ks - sigma_s_1 * sigma_s_1);
+      if (make_taps(sigma, 4.f, &S.stage_taps[s]) < 0)
+        return fail(ctx, SARA_B200_ERR_BAD_ARG, "Gaussian kernel of scale %d exceeds %d taps", s, kMaxTaps);
+      sigma_s_1 *= k;
+    }
+    return 0;
+  }
+
+  int check_slot(sara_b200_ctx* ctx, int slot)
+  {
+    if (!ctx)
+      return fail(nullptr, SARA_B200_ERR_BAD_ARG, "null context");
+    if (slot < 0 || slot >= static_cast<int>(ctx->slots.size()))
+      return fail(ctx, SARA_B200_ERR_BAD_ARG, "slot %d out of range [0, %d)", slot,
+                  static_cast<int>(ctx->slots.size()));
+    return 0;
+  }
+
+  // Gaussian pyramid + DoG pyramid of one frame.
+  int enqueue_pyramid(sara_b200_ctx* ctx, Slot& S, const float* image, int w, int h, bool on_device,
+                      const sara_b200_pyramid_params& pp, float gauss_truncate, cudaStream_t st)
+  {
+    Geometry g;
+    int rc = plan_geometry(ctx, w, h, pp, &g);
+    if (rc)
+      return rc;
+    rc = layout_slot(ctx, S, w, h, g, pp, on_device);
+    if (rc)
+      return rc;
+    S.stream = st;
+    S.pyramid_launches = 0;
+    const bool prof = ctx->profiling;
+    if (prof)
+      CU(ctx, cudaEventRecord(S.ev[0], st));
+    const float* d_src = image;
+    if (!on_device)
+    {
+      CU(ctx, cudaMemcpyAsync(S.d_img, image, sizeof(float) * w * h, cudaMemcpyHostToDevice, st));
+      d_src = S.d_img;
+    }
+    if (prof)
+      CU(ctx, cudaEventRecord(S.ev[1], st));
+    const PyramidDesc& P = S.P;
+    if (P.n_octaves > 0)
+    {
+      const OctaveDesc& o0 = P.oct[0];
+      if (pp.first_octave_index < 0)
+      {
+        launch_enlarge(d_src, w, h, w, o0.G, o0.w, o0.h, o0.pitch, st);
+        ++S.pyramid_launches;
+      }
+      else
+      {
+        Taps pre;
+        if (g.pre_sigma > 0.f)
+        {
+          // fo > 0 forwards gauss_truncate, fo == 0 uses the default 4 (GaussianPyramid.hpp:61,72).
+          const float trunc = pp.first_octave_index > 0 ? gauss_truncate : 4.f;
+          if (make_taps(g.pre_sigma, trunc, &pre) < 0)
+            return fail(ctx, SARA_B200_ERR_BAD_ARG, "pre-blur kernel exceeds %d taps", kMaxTaps);
+        }
+        if (g.pre_downscale > 0)
+        {
+          const float* full = d_src;
+          if (g.pre_sigma > 0.f)
+          {
+            launch_gaussian_stage(d_src, w, S.d_tmp, w, nullptr, 0, w, h, pre, st);
+            ++S.pyramid_launches;
+            full = S.d_tmp;
+          }
+          launch_downscale(full, w, h, w, o0.G, o0.w, o0.h, o0.pitch, st);
+        }
+        else if (g.pre_sigma > 0.f)
+          launch_gaussian_stage(d_src, w, o0.G, o0.pitch, nullptr, 0, w, h, pre, st);
+        else
+          launch_copy2d(d_src, w, o0.G, o0.pitch, w, h, st);
+        ++S.pyramid_launches;
+      }
+      const bool fused = fused_octave_supported(S.stage_taps.data(), P.n_scales);
+      for (int o = 0; o < P.n_octaves; ++o)
+      {
+        const OctaveDesc& oc = P.oct[o];
+        const OctaveDesc* next = o + 1 < P.n_octaves ? &P.oct[o + 1] : nullptr;
+        if (fused)
+        {
+          launch_fused_octave(oc, next, S.downscale_index, S.stage_taps.data(), P.n_scales, st);
+          ++S.pyramid_launches;
+          continue;
+        }
+        for (int s = 1; s < P.n_scales; ++s)
+        {
+          launch_gaussian_stage(oc.G + static_cast<size_t>(s - 1) * oc.layer_stride, oc.pitch,
+                                oc.G + static_cast<size_t>(s) * oc.layer_stride, oc.pitch,
+                                oc.D + static_cast<size_t>(s - 1) * oc.layer_stride, oc.pitch, oc.w, oc.h,
+                                S.stage_taps[s], st);
+          ++S.pyramid_launches;
+          if (next && s == S.downscale_index)
+          {
+            launch_downscale(oc.G + static_cast<size_t>(s) * oc.layer_stride, oc.w, oc.h, oc.pitch,
+                             next->G, next->w, next->h, next->pitch, st);
+            ++S.pyramid_launches;
+          }
+        }
+        if (next && S.downscale_index == 0)
+        {
+          launch_downscale(oc.G, oc.w, oc.h, oc.pitch, next->G, next->w, next->h, next->pitch, st);
+          ++S.pyramid_launches;
+        }
+      }
+    }
+    if (prof)
+      CU(ctx, cudaEventRecord(S.ev[2], st));
+    CU(ctx, cudaGetLastError());
+    S.total_launches = S.pyramid_launches;
+    return 0;
+  }
+
+  int enqueue_extrema(sara_b200_ctx* ctx, Slot& S, float extremum_thres, float edge_ratio, int pad,
+                      int refine_iter, cudaStream_t st)
+  {
+    if (S.P.n_scales < 4)  // DoG.hpp:86-89
+      return fail(ctx, SARA_B200_ERR_TOO_FEW_SCALES,
+                  "Error: The extraction of DoG extrema needs (1 + 3) = 4 scales per octave at the very "
+                  "minimum!");
+    if (pad < 1)
+      return fail(ctx, SARA_B200_ERR_BAD_ARG,
+                  "img_padding_sz must be >= 1 (the 3x3x3 neighbourhood must stay inside the layer)");
+    CU(ctx, cudaMemsetAsync(S.counters, 0, sizeof(Counters), st));
+    if (S.P.n_octaves > 0 && S.n_segments > 0)
+    {
+      ExtremaParams ep{extremum_thres, edge_ratio, pad, refine_iter};
+      S.total_launches += launch_extrema(S.P, ep, S.n_segments, S.seg_offsets, S.cand, ctx->cap_cand,
+                                         S.ext_tmp, nullptr, S.scratch, S.ext, ctx->cap_ext, S.counters, st);
+    }
+    if (ctx->profiling)
+      CU(ctx, cudaEventRecord(S.ev[3], st));
+    CU(ctx, cudaGetLastError());
+    return 0;
+  }
+
+  int enqueue_describe(sara_b200_ctx* ctx, Slot& S, cudaStream_t st)
+  {
+    if (S.P.n_octaves > 0)
+    {
+      S.total_launches += launch_orientation(S.P, S.ext, ctx->cap_ext, S.ori_count, S.oris, S.scratch,
+                                             S.kp_oct, ctx->cap_kp, S.counters, st);
+      if (ctx->profiling)
+        CU(ctx, cudaEventRecord(S.ev[4], st));
+      S.total_launches += launch_descriptors(S.P, S.kp_oct, S.kp_out, S.desc, ctx->cap_kp, S.counters, st);
+    }
+    else if (ctx->profiling)
+      CU(ctx, cudaEventRecord(S.ev[4], st));
+    if (ctx->profiling)
+      CU(ctx, cudaEventRecord(S.ev[5], st));
+    CU(ctx, cudaGetLastError());
+    return 0;
+  }
+
+  int finish_enqueue(sara_b200_ctx* ctx, Slot& S, cudaStream_t st)
+  {
+    CU(ctx, cudaMemcpyAsync(S.h_counters, S.counters, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    S.busy = true;
+    return 0;
+  }
+
+  int wait_slot(sara_b200_ctx* ctx, Slot& S)
+  {
+    CU(ctx, cudaStreamSynchronize(S.stream ? S.stream : S.own_stream));
+    if (ctx->profiling && S.busy)
+    {
+      auto ms = [&](int a, int b) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, S.ev[a], S.ev[b]);
+        return t;
+      };
+      S.timings = sara_b200_timings{};
+      S.timings.upload = ms(0, 1);
+      S.timings.pyramid = ms(1, 2);
+      if (S.has_keypoints)
+      {
+        S.timings.extrema = ms(2, 3);
+        S.timings.orientation = ms(3, 4);
+        S.timings.descriptor = ms(4, 5);
+        S.timings.total = ms(1, 5);
+      }
+      else
+        S.timings.total = ms(1, 2);
+      cudaGetLastError();
+    }
+    S.timings.pyramid_launches = S.pyramid_launches;
+    S.timings.total_launches = S.total_launches;
+    S.busy = false;
+    return 0;
+  }
+
+  int copy_keypoints(sara_b200_ctx* ctx, Slot& S, const Keypoint* d_src, int n_true, int cap_dev,
+                     sara_b200_keypoint* dst, int capacity, int* n_out)
+  {
+    if (n_out)
+      *n_out = n_true;
+    if (n_true > cap_dev)
+      return fail(ctx, SARA_B200_ERR_OVERFLOW, "%d entries exceed the context capacity %d", n_true, cap_dev);
+    if (n_true > capacity)
+      return fail(ctx, SARA_B200_ERR_OVERFLOW, "%d entries exceed the caller's capacity %d", n_true, capacity);
+    if (dst && n_true > 0)
+      CU(ctx, cudaMemcpy(dst, d_src, sizeof(Keypoint) * n_true, cudaMemcpyDeviceToHost));
+    return 0;
+  }
+
+}  // namespace
+
+// ============================================================================ //
+extern "C" {
+
+int sara_b200_version(void)
+{
+  return SARA_B200_VERSION;
+}
+
+const char* sara_b200_last_error(const sara_b200_ctx* ctx)
+{
+  return ctx ? ctx->err : g_create_error;
+}
+
+void sara_b200_default_pyramid_params(sara_b200_pyramid_params* p)
+{
+  p->first_octave_index = -1;
+  p->scale_count_per_octave = 3 + 3;
+  p->scale_geometric_factor = std::pow(2.f, 1.f / 3.f);
+  p->image_padding_size = 1;
+  p->scale_camera = 0.5f;
+  p->scale_initial = 1.6f;
+  p->num_octaves_max = INT_MAX;
+}
+
+void sara_b200_default_sift_args(sara_b200_sift_args* a)
+{
+  sara_b200_default_pyramid_params(&a->pyramid_params);
+  a->gauss_truncate = 4.f;
+  a->extremum_thres = 0.01f;
+  a->edge_ratio_thres = 10.f;
+  a->extremum_refinement_iter = 5;
+}
+
+void sara_b200_default_dog_args(sara_b200_dog_args* a)
+{
+  sara_b200_default_pyramid_params(&a->pyramid_params);
+  a->gauss_truncate = 4.f;
+  a->extremum_thres = 0.01f;
+  a->edge_ratio_thres = 10.f;
+  a->img_padding_sz = 1;
+  a->extremum_refinement_iter = 5;
+}
+
+int sara_b200_create(int device, const sara_b200_limits* limits, sara_b200_ctx** out)
+{
+  if (!out || !limits)
+    return fail(nullptr, SARA_B200_ERR_BAD_ARG, "null argument");
+  *out = nullptr;
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0)
+    return fail(nullptr, SARA_B200_ERR_CUDA,
+                "no usable CUDA device (%s); this library has no CPU path",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  if (device < 0 || device >= n_dev)
+    return fail(nullptr, SARA_B200_ERR_BAD_ARG, "device %d out of range [0, %d)", device, n_dev);
+  if (limits->max_width <= 0 || limits->max_height <= 0)
+    return fail(nullptr, SARA_B200_ERR_BAD_ARG, "limits: max_width / max_height must be positive");
+  CU(nullptr, cudaSetDevice(device));
+
+  auto* ctx = new sara_b200_ctx;
+  ctx->device = device;
+  ctx->lim = *limits;
+  ctx->cap_kp = limits->max_keypoints > 0 ? limits->max_keypoints : 262144;
+  if (ctx->cap_kp > 500000)
+    ctx->cap_kp = 500000;
+  ctx->cap_ext = ctx->cap_kp;
+  ctx->cap_cand = 2 * ctx->cap_kp;
+  const int n_slots = limits->num_slots > 0 ? limits->num_slots : 1;
+  ctx->slots.resize(n_slots);
+
+  for (Slot& S : ctx->slots)
+  {
+    cudaError_t err = cudaStreamCreateWithFlags(&S.own_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 7 && err == cudaSuccess; ++i)
+      err = cudaEventCreate(&S.ev[i]);
+    size_t bytes = 0;
+    auto take = [&](size_t n) {
+      const size_t off = bytes;
+      bytes = align_up(bytes + n, 256);
+      return off;
+    };
+    const size_t o_cand = take(sizeof(Candidate) * ctx->cap_cand);
+    const size_t o_tmp = take(sizeof(Keypoint) * ctx->cap_cand);
+    const size_t o_ext = take(sizeof(Keypoint) * ctx->cap_ext);
+    const size_t o_kpo = take(sizeof(Keypoint) * ctx->cap_kp);
+    const size_t o_kpf = take(sizeof(Keypoint) * ctx->cap_kp);
+    const size_t o_desc = take(sizeof(float) * 128 * ctx->cap_kp);
+    const size_t o_oc = take(sizeof(int) * ctx->cap_ext);
+    const size_t o_or = take(sizeof(float) * kMaxOri * ctx->cap_ext);
+    const size_t o_scr = take(sizeof(int) * (1024 + 2 * static_cast<size_t>(ctx->cap_cand)));
+    const size_t o_cnt = take(sizeof(Counters));
+    if (err == cudaSuccess)
+      err = cudaMalloc(&S.kbuf, bytes);
+    if (err == cudaSuccess)
+      err = cudaHostAlloc(&S.h_counters, sizeof(Counters), cudaHostAllocDefault);
+    if (err != cudaSuccess)
+    {
+      const int code = fail(nullptr, err == cudaErrorMemoryAllocation ? SARA_B200_ERR_OOM : SARA_B200_ERR_CUDA,
+                            "context creation failed: %s", cudaGetErrorString(err));
+      sara_b200_destroy(ctx);
+      return code;
+    }
+    S.cand = reinterpret_cast<Candidate*>(S.kbuf + o_cand);
+    S.ext_tmp = reinterpret_cast<Keypoint*>(S.kbuf + o_tmp);
+    S.ext = reinterpret_cast<Keypoint*>(S.kbuf + o_ext);
+    S.kp_oct = reinterpret_cast<Keypoint*>(S.kbuf + o_kpo);
+    S.kp_out = reinterpret_cast<Keypoint*>(S.kbuf + o_kpf);
+    S.desc = reinterpret_cast<float*>(S.kbuf + o_desc);
+    S.ori_count = reinterpret_cast<int*>(S.kbuf + o_oc);
+    S.oris = reinterpret_cast<float*>(S.kbuf + o_or);
+    S.scratch = reinterpret_cast<int*>(S.kbuf + o_scr);
+    S.counters = reinterpret_cast<Counters*>(S.kbuf + o_cnt);
+    std::memset(S.h_counters, 0, sizeof(Counters));
+    cudaMemset(S.counters, 0, sizeof(Counters));
+
+    // Size the pyramid arena for the largest frame up front (default scale count).
+    sara_b200_pyramid_params pp;
+    sara_b200_default_pyramid_params(&pp);
+    pp.first_octave_index = limits->min_first_octave_index < 0 ? limits->min_first_octave_index : 0;
+    Geometry g;
+    if (plan_geometry(ctx, limits->max_width, limits->max_height, pp, &g) == 0)
+    {
+      const int rc = layout_slot(ctx, S, limits->max_width, limits->max_height, g, pp, false);
+      if (rc)
+      {
+        std::memcpy(g_create_error, ctx->err, sizeof(g_create_error));
+        sara_b200_destroy(ctx);
+        return rc;
+      }
+    }
+    S.P = PyramidDesc{};
+  }
+  *out = ctx;
+  return 0;
+}
+
+void sara_b200_destroy(sara_b200_ctx* ctx)
+{
+  if (!ctx)
+    return;
+  cudaSetDevice(ctx->device);
+  for (Slot& S : ctx->slots)
+  {
+    if (S.own_stream)
+      cudaStreamSynchronize(S.own_stream);
+    if (S.stream && S.stream != S.own_stream && S.busy)
+      cudaStreamSynchronize(S.stream);
+    cudaFree(S.arena);
+    cudaFree(S.kbuf);
+    cudaFreeHost(S.h_counters);
+    for (auto& ev : S.ev)
+      if (ev)
+        cudaEventDestroy(ev);
+    if (S.own_stream)
+      cudaStreamDestroy(S.own_stream);
+  }
+  delete ctx;
+}
+
+int sara_b200_host_alloc(void** ptr, uint64_t bytes)
+{
+  if (!ptr)
+    return SARA_B200_ERR_BAD_ARG;
+  cudaError_t e = cudaHostAlloc(ptr, bytes, cudaHostAllocDefault);
+  if (e != cudaSuccess)
+    return fail(nullptr, SARA_B200_ERR_OOM, "cudaHostAlloc(%llu) failed: %s",
+                static_cast<unsigned long long>(bytes), cudaGetErrorString(e));
+  return 0;
+}
+
+void sara_b200_host_free(void* ptr)
+{
+  if (ptr)
+    cudaFreeHost(ptr);
+}
+
+int sara_b200_set_profiling(sara_b200_ctx* ctx, int on)
+{
+  if (!ctx)
+    return SARA_B200_ERR_BAD_ARG;
+  ctx->profiling = on != 0;
+  return 0;
+}
+
+int sara_b200_last_timings(sara_b200_ctx* ctx, int slot, sara_b200_timings* out)
+{
+  int rc = check_slot(ctx, slot);
+  if (rc)
+    return rc;
+  if (!out)
+    return fail(ctx, SARA_B200_ERR_BAD_ARG, "null output");
+  *out = ctx->slots[slot].timings;
+  return 0;
+}
+
+int sara_b200_sift_enqueue(sara_b200_ctx* ctx, int slot, const float* image, int w, int h,
+                           int image_on_device, const sara_b200_sift_args* args, void* stream)
+{
+  int rc = check_slot(ctx, slot);
+  if (rc)
+    return rc;
+  if (!image || !args)
+    return fail(ctx, SARA_B200_ERR_BAD_ARG, "null argument");
+  Slot& S = ctx->slots[slot];
+  if (S.busy)
+    return fail(ctx, SARA_B200_ERR_BUSY, "slot %d holds an un-collected frame", slot);
+  if (args->pyramid_params.scale_count_per_octave < 4)
+    return fail(ctx, SARA_B200_ERR_TOO_FEW_SCALES,
+                "Error: The extraction of DoG extrema needs (1 + 3) = 4 scales per octave at the very "
+                "minimum!");
+  CU(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : S.own_stream;
+  rc = enqueue_pyramid(ctx, S, image, w, h, image_on_device != 0, args->pyramid_params,
+                       args->gauss_truncate, st);
+  if (rc)
+    return rc;
+  // Quirk N1 (SIFT.cpp:45-51 vs DoG.hpp:72-78): extremum_refinement_iter lands in
+  // the img_padding_sz slot; the iteration count keeps its default, 5.
+  rc = enqueue_extrema(ctx, S, args->extremum_thres, args->edge_ratio_thres,
+                       args->extremum_refinement_iter, 5, st);
+  if (rc)
+    return rc;
+  rc = enqueue_describe(ctx, S, st);
+  if (rc)
+    return rc;
+  S.has_keypoints = true;
+  return finish_enqueue(ctx, S, st);
+}
+
+int sara_b200_wait(sara_b200_ctx* ctx, int slot, int* n_out)
+{
+  int rc = check_slot(ctx, slot);
+  if (rc)
+    return rc;
+  Slot& S = ctx->slots[slot];
+  rc = wait_slot(ctx, S);
+  if (rc)
+    return rc;
+  if (n_out)
+    *n_out = S.has_keypoints ? S.h_counters->n_kp : 0;
+  return 0;
+}
+
+int sara_b200_collect(sara_b200_ctx* ctx, int slot, sara_b200_keypoint* keypoints, float* descriptors,
+                      int capacity, int* n_out)
+{
+  int rc = check_slot(ctx, slot);
+  if (rc)
+    return rc;
+  Slot& S = ctx->slots[slot];
+  rc = wait_slot(ctx, S);
+  if (rc)
+    return rc;
+  const Counters c = *S.h_counters;
+  if (n_out)
+    *n_out = c.n_kp;
+  if (c.overflow)
+    return fail(ctx, SARA_B200_ERR_OVERFLOW,
+                "frame exceeds the context capacity (candidates %d, extrema %d, keypoints %d; max_keypoints %d)",
+                c.n_cand, c.n_ext, c.n_kp, ctx->cap_kp);
+  if (c.n_kp > capacity)
+    return fail(ctx, SARA_B200_ERR_OVERFLOW, "%d keypoints exceed the caller's capacity %d", c.n_kp, capacity);
+  cudaStream_t st = S.stream ? S.stream : S.own_stream;
+  if (c.n_kp > 0)
+  {
+    if (keypoints)
+      CU(ctx, cudaMemcpyAsync(keypoints, S.kp_out, sizeof(Keypoint) * c.n_kp, cudaMemcpyDeviceToHost, st));
+    if (descriptors)
+      CU(ctx, cudaMemcpyAsync(descriptors, S.desc, sizeof(float) * 128 * c.n_kp, cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+  }
+  return 0;
+}
+
+int sara_b200_device_results(sara_b200_ctx* ctx, int slot, const sara_b200_keypoint** keypoints,
+                             const float** descriptors, int* n_out)
+{
+  int rc = check_slot(ctx, slot);
+  if (rc)
+    return rc;
+  Slot& S = ctx->slots[slot];
+  rc = wait_slot(ctx, S);
+  if (rc)
+    return rc;
+  if (keypoints)
+    *keypoints = S.kp_out;
+  if (descriptors)
+    *descriptors = S.desc;
+  if (n_out)
+    *n_out = std::min(S.h_counters->n_kp, ctx->cap_kp);
+  return S.h_counters->overflow ? fail(ctx, SARA_B200_ERR_OVERFLOW, "frame exceeds the context capacity") : 0;
+}
+
+int sara_b200_sift(sara_b200_ctx* ctx, const float* image, int w, int h, int image_on_device,
+                   const sara_b200_sift_args* args, sara_b200_keypoint* keypoints, float* descriptors,
+                   int capacity, int* n_out)
+{
+  int rc = sara_b200_sift_enqueue(ctx, 0, image, w, h, image_on_device, args, nullptr);
+  if (rc)
+    return rc;
+  return sara_b200_collect(ctx, 0, keypoints, descriptors, capacity, n_out);
+}
+
+int sara_b200_dog_extrema(sara_b200_ctx* ctx, int slot, const float* image, int w, int h,
+                          int image_on_device, const sara_b200_dog_args* args)
+{
+  int rc = check_slot(ctx, slot);
+  if (rc)
+    return rc;
+  if (!image || !args)
+    return fail(ctx, SARA_B200_ERR_BAD_ARG, "null argument");
+  Slot& S = ctx->slots[slot];
+  if (S.busy)
+    return fail(ctx, SARA_B200_ERR_BUSY, "slot %d holds an un-collected frame", slot);
+  if (args->pyramid_params.scale_count_per_octave < 4)
+    return fail(ctx, SARA_B200_ERR_TOO_FEW_SCALES,
+                "Error: The extraction of DoG extrema needs (1 + 3) = 4 scales per octave at the very "
+                "minimum!");
+  CU(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = S.own_stream;
+  rc = enqueue_pyramid(ctx, S, image, w, h, image_on_device != 0, args->pyramid_params,
+                       args->gauss_truncate, st);
+  if (rc)
+    return rc;
+  rc = enqueue_extrema(ctx, S, args->extremum_thres, args->edge_ratio_thres, args->img_padding_sz,
+                       args->extremum_refinement_iter, st);
+  if (rc)
+    return rc;
+  S.has_keypoints = false;
+  rc = finish_enqueue(ctx, S, st);
+  if (rc)
+    return rc;
+  return wait_slot(ctx, S);
+}
+
+int sara_b200_pyramid_enqueue(sara_b200_ctx* ctx, int slot, const float* image, int w, int h,
+                              int image_on_device, const sara_b200_pyramid_params* params,
+                              float gauss_truncate, void* stream)
+{
+  int rc = check_slot(ctx, slot);
+  if (rc)
+    return rc;
+  if (!image || !params)
+    return fail(ctx, SARA_B200_ERR_BAD_ARG, "null argument");
+  Slot& S = ctx->slots[slot];
+  if (S.busy)
+    return fail(ctx, SARA_B200_ERR_BUSY, "slot %d holds an un-collected frame", slot);
+  CU(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : S.own_stream;
+  rc = enqueue_pyramid(ctx, S, image, w, h, image_on_device != 0, *params, gauss_truncate, st);
+  if (rc)
+    return rc;
+  S.has_keypoints = false;
+  std::memset(S.h_counters, 0, sizeof(Counters));
+  S.busy = true;
+  return 0;
+}
+
+int sara_b200_num_octaves(sara_b200_ctx* ctx, int slot)
+{
+  return check_slot(ctx, slot) ? -1 : ctx->slots[slot].P.n_octaves;
+}
+
+int sara_b200_num_scales(sara_b200_ctx* ctx, int slot)
+{
+  return check_slot(ctx, slot) ? -1 : ctx->slots[slot].P.n_scales;
+}
+
+int sara_b200_layer_size(sara_b200_ctx* ctx, int slot, int octave, int* w, int* h)
+{
+  int rc = check_slot(ctx, slot);
+  if (rc)
+    return rc;
+  const PyramidDesc& P = ctx->slots[slot].P;
+  if (octave < 0 || octave >= P.n_octaves)
+    return fail(ctx, SARA_B200_ERR_BAD_ARG, "octave %d out of range [0, %d)", octave, P.n_octaves);
+  if (w)
+    *w = P.oct[octave].w;
+  if (h)
+    *h = P.oct[octave].h;
+  return 0;
+}
+
+float sara_b200_octave_scaling_factor(sara_b200_ctx* ctx, int slot, int octave)
+{
+  if (check_slot(ctx, slot))
+    return 0.f;
+  const PyramidDesc& P = ctx->slots[slot].P;
+  if (octave < 0 || octave >= P.n_octaves)
+    return 0.f;
+  return P.oct[octave].scaling;
+}
+
+int sara_b200_copy_layer(sara_b200_ctx* ctx, int slot, int which, int s, int o, float* dst)
+{
+  int rc = check_slot(ctx, slot);
+  if (rc)
+    return rc;
+  Slot& S = ctx->slots[slot];
+  const PyramidDesc& P = S.P;
+  if (!dst || o < 0 || o >= P.n_octaves || s < 0 || s >= (which == 0 ? P.n_scales : P.n_scales - 1) ||
+      (which != 0 && which != 1))
+    return fail(ctx, SARA_B200_ERR_BAD_ARG, "copy_layer: bad (which=%d, s=%d, o=%d)", which, s, o);  // std::out_of_range in ImagePyramid
+  rc = wait_slot(ctx, S);
+  if (rc)
+    return rc;
+  const OctaveDesc& oc = P.oct[o];
+  const float* src = (which == 0 ? oc.G : oc.D) + static_cast<size_t>(s) * oc.layer_stride;
+  CU(ctx, cudaMemcpy2D(dst, sizeof(float) * oc.w, src, sizeof(float) * oc.pitch, sizeof(float) * oc.w, oc.h,
+                       cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int sara_b200_copy_extrema(sara_b200_ctx* ctx, int slot, sara_b200_keypoint* dst, int capacity, int* n_out)
+{
+  int rc = check_slot(ctx, slot);
+  if (rc)
+    return rc;
+  Slot& S = ctx->slots[slot];
+  rc = wait_slot(ctx, S);
+  if (rc)
+    return rc;
+  return copy_keypoints(ctx, S, S.ext, S.h_counters->n_ext, ctx->cap_ext, dst, capacity, n_out);
+}
+
+int sara_b200_copy_oriented(sara_b200_ctx* ctx, int slot, sara_b200_keypoint* dst, int capacity, int* n_out)
+{
+  int rc = check_slot(ctx, slot);
+  if (rc)
+    return rc;
+  Slot& S = ctx->slots[slot];
+  rc = wait_slot(ctx, S);
+  if (rc)
+    return rc;
+  const int n = S.has_keypoints ? S.h_counters->n_kp : 0;
+  return copy_keypoints(ctx, S, S.kp_oct, n, ctx->cap_kp, dst, capacity, n_out);
+}
+
+int sara_b200_gaussian(sara_b200_ctx* ctx, const float* src, int w, int h, float sigma, float gauss_truncate,
+                       float* dst)
+{
+  if (!ctx)
+    return fail(nullptr, SARA_B200_ERR_BAD_ARG, "null context");
+  if (!src || !dst || w <= 0 || h <= 0)
+    return fail(ctx, SARA_B200_ERR_BAD_ARG, "gaussian: bad arguments");
+  Taps taps;
+  if (make_taps(sigma, gauss_truncate, &taps) < 0)
+    return fail(ctx, SARA_B200_ERR_BAD_ARG, "Gaussian kernel exceeds %d taps", kMaxTaps);
+  CU(ctx, cudaSetDevice(ctx->device));
+  float *d_a = nullptr, *d_b = nullptr;
+  const size_t bytes = sizeof(float) * w * h;
+  CU(ctx, cudaMalloc(&d_a, bytes));
+  cudaError_t e = cudaMalloc(&d_b, bytes);
+  if (e != cudaSuccess)
+  {
+    cudaFree(d_a);
+    return fail(ctx, SARA_B200_ERR_OOM, "cudaMalloc failed: %s", cudaGetErrorString(e));
+  }
+  cudaStream_t st = ctx->slots[0].own_stream;
+  cudaMemcpyAsync(d_a, src, bytes, cudaMemcpyHostToDevice, st);
+  launch_gaussian_stage(d_a, w, d_b, w, nullptr, 0, w, h, taps, st);
+  cudaMemcpyAsync(dst, d_b, bytes, cudaMemcpyDeviceToHost, st);
+  e = cudaStreamSynchronize(st);
+  cudaFree(d_a);
+  cudaFree(d_b);
+  if (e != cudaSuccess)
+    return fail(ctx, SARA_B200_ERR_CUDA, "gaussian failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int sara_b200_make_gaussian_kernel(float sigma, float gauss_truncate, float* taps, int capacity)
+{
+  Taps t;
+  const int n = make_taps(sigma, gauss_truncate, &t);
+  if (n < 0)
+    return n;
+  if (n > capacity || !taps)
+    return -n;
+  std::memcpy(taps, t.v, sizeof(float) * n);
+  return n;
+}
+
+}  // extern "C"

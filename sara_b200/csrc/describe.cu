@@ -1,0 +1,369 @@
+// Dominant orientations and 128-D SIFT descriptors, one warp per keypoint.
+//
+// Restates the behaviour of
+//   gradient_polar_coordinates      FeatureDescriptors/Orientation.cpp:24-56,
+//                                   ImageProcessing/Differential.hpp:46-61
+//   compute_orientation_histogram   FeatureDescriptors/Orientation.hpp:91-139
+//   lowe_smooth_histogram           Orientation.hpp:147-165
+//   find_peaks / refine_peak        Orientation.hpp:176-214
+//   ComputeDominantOrientations     Orientation.cpp:90-166
+//   ComputeSIFTDescriptor<4, 8>     FeatureDescriptors/SIFT.hpp:62-145, 204-258
+//   rescale to image coordinates    FeatureDetectors/SIFT.cpp:92-98
+//
+// The reference materialises a polar-gradient pyramid (magnitude, atan2) for
+// all 6 layers of every octave; here the gradient is evaluated on the fly from
+// the Gaussian layer G(s, o) for just the samples a keypoint touches.
+//
+// Determinism: every lane accumulates into a private shared-memory histogram
+// (no floating-point atomics), then the 32 partials of each bin are summed in a
+// fixed order, so the same frame always yields the same bits.  Relative to the
+// CPU path the SUMMATION ORDER differs (raster order there), and atan2f / expf
+// are CUDA's, so orientations and descriptors are compared with a tolerance.
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace sb {
+
+  namespace {
+
+    constexpr float kPi = 3.14159274101257324f;     // float(M_PI)
+    constexpr float kTwoPi = 6.28318548202514648f;  // float(2. * M_PI)
+
+    // Polar gradient at (x, y) of layer f: (2 * |g|, atan2(gy, gx)) with the
+    // one-sided differences of the Gradient functor at the borders.
+    __device__ __forceinline__ void polar_gradient(const float* __restrict__ f, int w, int h, int pitch,
+                                                   int x, int y, float& mag, float& ori)
+    {
+      const float* row = f + static_cast<size_t>(y) * pitch;
+      const int xn = x == w - 1 ? x : x + 1;
+      const int xp = x == 0 ? x : x - 1;
+      const int yn = y == h - 1 ? y : y + 1;
+      const int yp = y == 0 ? y : y - 1;
+      const float gx = __fdiv_rn(__fsub_rn(__ldg(row + xn), __ldg(row + xp)), 2.f);
+      const float gy = __fdiv_rn(__fsub_rn(__ldg(f + static_cast<size_t>(yn) * pitch + x),
+                                           __ldg(f + static_cast<size_t>(yp) * pitch + x)),
+                                 2.f);
+      mag = __fmul_rn(2.f, __fsqrt_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy))));
+      ori = atan2f(gy, gx);
+    }
+
+    constexpr int ORI_WARPS = 8;
+
+    __global__ void __launch_bounds__(ORI_WARPS * 32)
+        orientation_kernel(const __grid_constant__ PyramidDesc P, const Keypoint* __restrict__ ext,
+                           const Counters* __restrict__ counters, int cap_ext,
+                           int* __restrict__ ori_count, float* __restrict__ oris)
+    {
+      __shared__ float s_priv[ORI_WARPS][36][32];
+      __shared__ float s_hist[ORI_WARPS][2][36];
+      const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+      const int n = min(counters->n_ext, cap_ext);
+      const int warps_per_grid = gridDim.x * ORI_WARPS;
+      float(*priv)[32] = s_priv[wid];
+
+      for (int i = blockIdx.x * ORI_WARPS + wid; i < n; i += warps_per_grid)
+      {
+        const Keypoint kp = ext[i];
+        const OctaveDesc& oc = P.oct[kp.o];
+        const float* G = oc.G + static_cast<size_t>(kp.s) * oc.layer_stride;
+        const int w = oc.w, h = oc.h, pitch = oc.pitch;
+
+        // Orientation.cpp:150-157: the DISCRETE scale of the layer, not the refined one.
+        const float scale = P.scale_rel[kp.s];
+        const float sigma = __fmul_rn(scale, 1.5f);
+        const int rx = static_cast<int>(roundf(kp.x));
+        const int ry = static_cast<int>(roundf(kp.y));
+        const int radius = static_cast<int>(roundf(__fmul_rn(sigma, 3.f)));
+        const float denom = __fmul_rn(__fmul_rn(2.f, sigma), sigma);
+
+#pragma unroll
+        for (int b = 0; b < 36; ++b)
+          priv[b][lane] = 0.f;
+
+        const int side = 2 * radius + 1;
+        const int count = side * side;
+        for (int t = lane; t < count; t += 32)
+        {
+          const int v = t / side - radius;
+          const int u = t - (v + radius) * side - radius;
+          const int X = rx + u, Y = ry + v;
+          if (X < 0 || X >= w || Y < 0 || Y >= h)
+            continue;
+          float mag, ori;
+          polar_gradient(G, w, h, pitch, X, Y, mag, ori);
+          ori = ori < 0.f ? __fadd_rn(ori, kTwoPi) : ori;
+          int bin = static_cast<int>(floorf(__fmul_rn(__fdiv_rn(ori, kTwoPi), 36.f)));
+          bin %= 36;
+          const float weight = expf(__fdiv_rn(static_cast<float>(-(u * u + v * v)), denom));
+          priv[bin][lane] = __fadd_rn(priv[bin][lane], __fmul_rn(weight, mag));
+        }
+        __syncwarp();
+
+        // Fixed-order reduction of the 32 partials of each bin.
+        float* h0 = s_hist[wid][0];
+        float* h1 = s_hist[wid][1];
+        for (int b = lane; b < 36; b += 32)
+        {
+          float sum = 0.f;
+#pragma unroll 8
+          for (int j = 0; j < 32; ++j)
+            sum = __fadd_rn(sum, priv[b][(j + lane) & 31]);
+          h0[b] = sum;
+        }
+        __syncwarp();
+
+        // lowe_smooth_histogram, 6 iterations: new[i] = ((old[i-1] + old[i]) + old[i+1]) / 3.
+        for (int iter = 0; iter < 6; ++iter)
+        {
+          for (int b = lane; b < 36; b += 32)
+          {
+            const float prev = h0[b == 0 ? 35 : b - 1];
+            const float next = h0[b == 35 ? 0 : b + 1];
+            h1[b] = __fdiv_rn(__fadd_rn(__fadd_rn(prev, h0[b]), next), 3.f);
+          }
+          __syncwarp();
+          float* t = h0;
+          h0 = h1;
+          h1 = t;
+        }
+
+        // find_peaks + refine_peak.
+        float mx = fmaxf(h0[lane], lane < 4 ? h0[32 + lane] : h0[lane]);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1)
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+        const float thres = __fmul_rn(0.8f, mx);
+        int n_peaks = 0;
+        for (int base = 0; base < 36; base += 32)
+        {
+          const int b = base + lane;
+          bool is_peak = false;
+          float y0 = 0.f, y1 = 0.f, y2 = 0.f;
+          if (b < 36)
+          {
+            y0 = h0[b == 0 ? 35 : b - 1];
+            y1 = h0[b];
+            y2 = h0[b == 35 ? 0 : b + 1];
+            is_peak = y1 >= thres && y1 > y0 && y1 > y2;
+          }
+          const unsigned m = __ballot_sync(0xffffffffu, is_peak);
+          if (is_peak)
+          {
+            const int slot = n_peaks + __popc(m & ((1u << lane) - 1u));
+            const float fprime = __fdiv_rn(__fsub_rn(y2, y0), 2.f);
+            const float fsecond = __fadd_rn(__fsub_rn(y0, __fmul_rn(2.f, y1)), y2);
+            const float hh = __fdiv_rn(-fprime, fsecond);
+            float p = __fadd_rn(__fadd_rn(static_cast<float>(b), 0.5f), hh);
+            p = __fmul_rn(p, __fdiv_rn(kTwoPi, 36.f));
+            if (p > kPi)
+              p = __fsub_rn(p, __fmul_rn(2.f, kPi));
+            if (slot < kMaxOri)
+              oris[static_cast<size_t>(i) * kMaxOri + slot] = p;
+          }
+          n_peaks += __popc(m);
+        }
+        if (lane == 0)
+          ori_count[i] = min(n_peaks, kMaxOri);
+        __syncwarp();
+      }
+    }
+
+    // Ordered expansion: keypoint i is emitted ori_count[i] times (Orientation.cpp:158-163).
+    __global__ void __launch_bounds__(256)
+        expand_kernel(const Keypoint* __restrict__ ext, const int* __restrict__ ori_count,
+                      const float* __restrict__ oris, const int* __restrict__ off,
+                      const int* __restrict__ chunk_off, const Counters* __restrict__ counters,
+                      int cap_ext, Keypoint* __restrict__ kp_oct, int cap_kp)
+    {
+      const int n = min(counters->n_ext, cap_ext);
+      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+      {
+        const int c = ori_count[i];
+        if (c == 0)
+          continue;
+        Keypoint kp = ext[i];
+        const int pos = off[i] + chunk_off[i >> 10];
+        for (int j = 0; j < c; ++j)
+          if (pos + j < cap_kp)
+          {
+            kp.orientation = oris[static_cast<size_t>(i) * kMaxOri + j];
+            kp_oct[pos + j] = kp;
+          }
+      }
+    }
+
+    constexpr int DESC_WARPS = 4;
+
+    __global__ void __launch_bounds__(DESC_WARPS * 32)
+        descriptor_kernel(const __grid_constant__ PyramidDesc P, const Keypoint* __restrict__ kp_oct,
+                          const Counters* __restrict__ counters, int cap_kp,
+                          Keypoint* __restrict__ kp_out, float* __restrict__ desc)
+    {
+      extern __shared__ float s_dyn[];  // DESC_WARPS x 128 x 32 lane-private bins
+      const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+      float* priv = s_dyn + wid * (128 * 32);
+      const int n = min(counters->n_kp, cap_kp);
+      const int warps_per_grid = gridDim.x * DESC_WARPS;
+
+      for (int i = blockIdx.x * DESC_WARPS + wid; i < n; i += warps_per_grid)
+      {
+        const Keypoint kp = kp_oct[i];
+        const OctaveDesc& oc = P.oct[kp.o];
+        const float* G = oc.G + static_cast<size_t>(kp.s) * oc.layer_stride;
+        const int w = oc.w, h = oc.h, pitch = oc.pitch;
+
+        // OERegion::scale() -> radius(), Features/Feature.cpp:28-39, for shape = a * I.
+        const float rr = __fdiv_rn(1.f, __fsqrt_rn(kp.shape[0]));
+        const float s = __fsqrt_rn(__fadd_rn(__fmul_rn(rr, rr), 0.f));
+        const float theta = kp.orientation;
+        const float l = __fmul_rn(3.f, s);
+        const float r = __fdiv_rn(__fmul_rn(__fmul_rn(__fsqrt_rn(2.f), l), 5.f), 2.f);
+        // cosf / sinf evaluated in double and rounded: agrees with a correctly rounded libm.
+        const float ct = static_cast<float>(cos(static_cast<double>(theta)));
+        const float st = static_cast<float>(sin(static_cast<double>(theta)));
+        const float T00 = __fdiv_rn(ct, l), T01 = __fdiv_rn(st, l);
+        const float T10 = __fdiv_rn(-st, l), T11 = __fdiv_rn(ct, l);
+        const int rounded_r = static_cast<int>(roundf(r));
+        const int rx = static_cast<int>(roundf(kp.x));
+        const int ry = static_cast<int>(roundf(kp.y));
+
+        for (int b = 0; b < 128; ++b)
+          priv[b * 32 + lane] = 0.f;
+
+        const int side = 2 * rounded_r + 1;
+        const int count = side * side;
+        for (int t = lane; t < count; t += 32)
+        {
+          const int v = t / side - rounded_r;
+          const int u = t - (v + rounded_r) * side - rounded_r;
+          const int X = rx + u, Y = ry + v;
+          if (X < 0 || X >= w || Y < 0 || Y >= h)
+            continue;
+          const float fu = static_cast<float>(u), fv = static_cast<float>(v);
+          float px = __fadd_rn(__fmul_rn(T00, fu), __fmul_rn(T01, fv));
+          float py = __fadd_rn(__fmul_rn(T10, fu), __fmul_rn(T11, fv));
+          const float wexp = __fdiv_rn(-__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), 8.f);
+          px = __fadd_rn(px, 1.5f);
+          py = __fadd_rn(py, 1.5f);
+          if (fminf(px, py) <= -1.f || fmaxf(px, py) >= 4.f)
+            continue;
+          const float weight = expf(wexp);
+          float mag, ori;
+          polar_gradient(G, w, h, pitch, X, Y, mag, ori);
+          ori = __fsub_rn(ori, theta);
+          ori = ori < 0.f ? __fadd_rn(ori, __fmul_rn(2.f, kPi)) : ori;
+          ori = __fmul_rn(ori, __fdiv_rn(8.f, __fmul_rn(2.f, kPi)));
+
+          // accumulate(), SIFT.hpp:204-238: std::modf truncates toward zero (quirk N6).
+          const float xif = truncf(px), yif = truncf(py), oif = truncf(ori);
+          const float xfrac = __fsub_rn(px, xif), yfrac = __fsub_rn(py, yif), ofrac = __fsub_rn(ori, oif);
+          const int xi = static_cast<int>(xif), yi = static_cast<int>(yif), oi = static_cast<int>(oif);
+#pragma unroll
+          for (int dy = 0; dy < 2; ++dy)
+          {
+            const int yy = yi + dy;
+            if (yy < 0 || yy >= 4)
+              continue;
+            const float wy = dy == 0 ? __fsub_rn(1.f, yfrac) : yfrac;
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx)
+            {
+              const int xx = xi + dx;
+              if (xx < 0 || xx >= 4)
+                continue;
+              const float wx = dx == 0 ? __fsub_rn(1.f, xfrac) : xfrac;
+#pragma unroll
+              for (int dori = 0; dori < 2; ++dori)
+              {
+                const int oo = (oi + dori) % 8;
+                const float wo = dori == 0 ? __fsub_rn(1.f, ofrac) : ofrac;
+                const float contrib =
+                    __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(wy, wx), wo), weight), mag);
+                float* bin = priv + (32 * yy + xx * 8 + oo) * 32 + lane;
+                *bin = __fadd_rn(*bin, contrib);
+              }
+            }
+          }
+        }
+        __syncwarp();
+
+        // Fixed-order reduction: lane owns bins lane, lane+32, lane+64, lane+96.
+        float hv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+        {
+          const float* pb = priv + (q * 32 + lane) * 32;
+          float sum = 0.f;
+#pragma unroll 8
+          for (int j = 0; j < 32; ++j)
+            sum = __fadd_rn(sum, pb[(j + lane) & 31]);
+          hv[q] = sum;
+        }
+        __syncwarp();
+
+        // normalize(): L2, clamp at 0.2, L2 (SIFT.hpp:241-252); then * 512, min 255 (SIFT.hpp:128).
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass)
+        {
+          float sq = __fadd_rn(__fadd_rn(__fmul_rn(hv[0], hv[0]), __fmul_rn(hv[1], hv[1])),
+                               __fadd_rn(__fmul_rn(hv[2], hv[2]), __fmul_rn(hv[3], hv[3])));
+#pragma unroll
+          for (int d = 16; d > 0; d >>= 1)
+            sq = __fadd_rn(sq, __shfl_xor_sync(0xffffffffu, sq, d));
+          const float nrm = __fsqrt_rn(sq);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+          {
+            hv[q] = __fdiv_rn(hv[q], nrm);
+            if (pass == 0)
+              hv[q] = fminf(hv[q], 0.2f);
+          }
+        }
+        float* out = desc + static_cast<size_t>(i) * 128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          out[q * 32 + lane] = fminf(__fmul_rn(hv[q], 512.f), 255.f);
+
+        if (lane == 0)
+        {
+          // SIFT.cpp:92-98: back to image coordinates.
+          Keypoint f = kp;
+          const float z = oc.scaling;
+          f.x = __fmul_rn(f.x, z);
+          f.y = __fmul_rn(f.y, z);
+          const float z2 = __fmul_rn(z, z);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            f.shape[j] = __fdiv_rn(f.shape[j], z2);
+          kp_out[i] = f;
+        }
+      }
+    }
+
+  }  // namespace
+
+  int launch_orientation(const PyramidDesc& P, const Keypoint* ext, int cap_ext, int* ori_count,
+                         float* oris, int* scratch, Keypoint* kp_oct, int cap_kp, Counters* counters,
+                         cudaStream_t st)
+  {
+    int* chunk_off = scratch;
+    int* ori_off = scratch + 1024;
+    orientation_kernel<<<148 * 4, ORI_WARPS * 32, 0, st>>>(P, ext, counters, cap_ext, ori_count, oris);
+    int launches = 1;
+    launches += exclusive_scan(ori_count, ori_off, chunk_off, 0, &counters->n_ext, cap_ext,
+                               &counters->n_kp, cap_kp, &counters->overflow, 4, st);
+    expand_kernel<<<296, 256, 0, st>>>(ext, ori_count, oris, ori_off, chunk_off, counters, cap_ext, kp_oct,
+                                       cap_kp);
+    return launches + 1;
+  }
+
+  int launch_descriptors(const PyramidDesc& P, const Keypoint* kp_oct, Keypoint* kp_out, float* desc,
+                         int cap_kp, Counters* counters, cudaStream_t st)
+  {
+    const int smem = DESC_WARPS * 128 * 32 * sizeof(float);
+    cudaFuncSetAttribute(descriptor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    descriptor_kernel<<<148 * 3, DESC_WARPS * 32, smem, st>>>(P, kp_oct, counters, cap_kp, kp_out, desc);
+    return 1;
+  }
+
+}  // namespace sb

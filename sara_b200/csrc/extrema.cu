@@ -1,0 +1,424 @@
+// Scale-space extrema of the DoG pyramid: classification, ORDERED compaction
+// (the list order must equal the reference's raster order), sub-pixel
+// refinement and the final threshold rejection.
+//
+// Restates (not copies) the behaviour of
+//   local_scale_space_extrema   FeatureDetectors/RefineExtremum.cpp:363-521
+//   refine_extremum (3-D)       FeatureDetectors/RefineExtremum.cpp:32-130
+//   on_edge                     FeatureDetectors/RefineExtremum.cpp:24-30
+//   LocalScaleSpaceExtremum     ImageProcessing/Extrema.hpp:28-75
+// including the reference quirks N2 (uint8 map: minima typed 255, never
+// refined), N7 (emitted at the original raster slot) and N8 (D', h carried
+// over when a later iteration leaves the domain).  Compiled with -fmad=false;
+// every decision is taken on bit-identical fp32 values, so the integer outputs
+// (x, y, s, o, type) are exact.
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace sb {
+
+  namespace {
+
+    __device__ __forceinline__ float ld(const float* p, int pitch, int x, int y)
+    {
+      return __ldg(p + static_cast<size_t>(y) * pitch + x);
+    }
+
+    // ---- pass 1: classify every pixel of D(s, o), s = 1 .. n_scales - 3 ------
+    __global__ void __launch_bounds__(256)
+        classify_kernel(const OctaveDesc oct, const ExtremaParams ep)
+    {
+      const int x = blockIdx.x * 32 + threadIdx.x;
+      const int y = blockIdx.y * 8 + threadIdx.y;
+      const int s = blockIdx.z + 1;
+      const int w = oct.w, h = oct.h, pitch = oct.pitch;
+      if (y >= h)
+        return;
+      uint8_t type = 0;
+      const bool in_domain = x < w && ep.pad <= x && x < w - ep.pad && ep.pad <= y && y < h - ep.pad;
+      if (in_domain)
+      {
+        const float* Dc = oct.D + static_cast<size_t>(s) * oct.layer_stride;
+        const float v = ld(Dc, pitch, x, y);
+        // All three rejections are ANDed in the reference; the cheap threshold
+        // test goes first.
+        if (!(fabsf(v) < __fmul_rn(0.8f, ep.extremum_thres)))
+        {
+          const float* Dp = Dc - oct.layer_stride;
+          const float* Dn = Dc + oct.layer_stride;
+          bool is_max = true, is_min = true;
+#pragma unroll
+          for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx)
+            {
+              const float a = ld(Dp, pitch, x + dx, y + dy);
+              const float b = ld(Dn, pitch, x + dx, y + dy);
+              is_max = is_max && (v >= a) && (v >= b);
+              is_min = is_min && (v <= a) && (v <= b);
+              if (dx != 0 || dy != 0)
+              {
+                const float cc = ld(Dc, pitch, x + dx, y + dy);
+                is_max = is_max && (v >= cc);
+                is_min = is_min && (v <= cc);
+              }
+            }
+          if (is_max || is_min)
+          {
+            // on_edge(): Hessian functor, ImageProcessing/Differential.hpp:191-226.
+            const float c2 = __fmul_rn(2.f, v);
+            const float hxx = __fadd_rn(__fsub_rn(ld(Dc, pitch, x + 1, y), c2), ld(Dc, pitch, x - 1, y));
+            const float hyy = __fadd_rn(__fsub_rn(ld(Dc, pitch, x, y + 1), c2), ld(Dc, pitch, x, y - 1));
+            const float hxy =
+                __fdiv_rn(__fadd_rn(__fsub_rn(__fsub_rn(ld(Dc, pitch, x + 1, y + 1),
+                                                        ld(Dc, pitch, x - 1, y + 1)),
+                                              ld(Dc, pitch, x + 1, y - 1)),
+                                    ld(Dc, pitch, x - 1, y - 1)),
+                          4.f);
+            const float tr = __fadd_rn(hxx, hyy);
+            const float det = __fsub_rn(__fmul_rn(hxx, hyy), __fmul_rn(hxy, hxy));
+            const float e1 = __fadd_rn(ep.edge_ratio, 1.f);
+            const bool edge =
+                __fmul_rn(__fmul_rn(tr, tr), ep.edge_ratio) >= __fmul_rn(__fmul_rn(e1, e1), fabsf(det));
+            if (!edge)
+              type = is_max ? 1 : 255;  // maximum is tested first (RefineExtremum.cpp:419-426)
+          }
+        }
+      }
+      if (x < w)
+        oct.map[(static_cast<size_t>(s - 1) * h + y) * w + x] = type;
+      const unsigned m = __ballot_sync(0xffffffffu, type != 0);
+      if (threadIdx.x == 0 && m != 0)
+        atomicAdd(oct.row_count + (s - 1) * h + y, __popc(m));
+    }
+
+    // ---- ordered compaction: one warp per raster row -------------------------
+    __global__ void __launch_bounds__(256)
+        compact_rows_kernel(const __grid_constant__ PyramidDesc P, int n_segments,
+                            const int* __restrict__ seg_off, const int* __restrict__ seg_chunk_off,
+                            Candidate* __restrict__ cand, int cap_cand)
+    {
+      const int lane = threadIdx.x & 31;
+      const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+      for (int seg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; seg < n_segments;
+           seg += warps_per_grid)
+      {
+        int o = 0;
+        while (o + 1 < P.n_octaves && seg >= P.oct[o + 1].seg_base)
+          ++o;
+        const OctaveDesc& oc = P.oct[o];
+        const int r = seg - oc.seg_base;
+        const int s = r / oc.h + 1;
+        const int y = r - (s - 1) * oc.h;
+        if (oc.row_count[r] == 0)
+          continue;
+        int out = seg_off[seg] + seg_chunk_off[seg >> 10];
+        const uint8_t* row = oc.map + (static_cast<size_t>(s - 1) * oc.h + y) * oc.w;
+        for (int x0 = 0; x0 < oc.w; x0 += 32)
+        {
+          const int x = x0 + lane;
+          const uint8_t t = x < oc.w ? row[x] : 0;
+          const unsigned m = __ballot_sync(0xffffffffu, t != 0);
+          if (t != 0)
+          {
+            const int pos = out + __popc(m & ((1u << lane) - 1u));
+            if (pos < cap_cand)
+              cand[pos] = Candidate{x, y, (o << 8) | s, t};
+          }
+          out += __popc(m);
+        }
+      }
+    }
+
+    // ---- refinement ------------------------------------------------------------
+    struct Sampler
+    {
+      const float* base;
+      int pitch, stride;
+      __device__ __forceinline__ float operator()(int x, int y, int s) const
+      {
+        return __ldg(base + static_cast<size_t>(s) * stride + static_cast<size_t>(y) * pitch + x);
+      }
+    };
+
+    // Sign pattern of the eigenvalues of a symmetric 3x3: cyclic Jacobi in fp32
+    // with +,-,*,/,sqrt only (the operations the CPU check repeats bit for bit);
+    // stands in for Eigen::SelfAdjointEigenSolver (RefineExtremum.cpp:74-81).
+    __device__ void sym3_eigenvalues(const float H[9], float lambda[3])
+    {
+      float a00 = H[0], a11 = H[4], a22 = H[8];
+      float a01 = H[1], a02 = H[2], a12 = H[5];
+#pragma unroll 1
+      for (int sweep = 0; sweep < 8; ++sweep)
+      {
+        if (a01 == 0.f && a02 == 0.f && a12 == 0.f)
+          break;
+        if (a01 != 0.f)
+        {
+          const float theta = __fdiv_rn(__fsub_rn(a11, a00), __fmul_rn(2.f, a01));
+          float t = __fdiv_rn(1.f, __fadd_rn(fabsf(theta), __fsqrt_rn(__fadd_rn(__fmul_rn(theta, theta), 1.f))));
+          if (theta < 0.f)
+            t = -t;
+          const float c = __fdiv_rn(1.f, __fsqrt_rn(__fadd_rn(__fmul_rn(t, t), 1.f)));
+          const float sn = __fmul_rn(t, c);
+          const float tau = __fmul_rn(t, a01);
+          a00 = __fsub_rn(a00, tau);
+          a11 = __fadd_rn(a11, tau);
+          a01 = 0.f;
+          const float b02 = __fsub_rn(__fmul_rn(c, a02), __fmul_rn(sn, a12));
+          const float b12 = __fadd_rn(__fmul_rn(sn, a02), __fmul_rn(c, a12));
+          a02 = b02;
+          a12 = b12;
+        }
+        if (a02 != 0.f)
+        {
+          const float theta = __fdiv_rn(__fsub_rn(a22, a00), __fmul_rn(2.f, a02));
+          float t = __fdiv_rn(1.f, __fadd_rn(fabsf(theta), __fsqrt_rn(__fadd_rn(__fmul_rn(theta, theta), 1.f))));
+          if (theta < 0.f)
+            t = -t;
+          const float c = __fdiv_rn(1.f, __fsqrt_rn(__fadd_rn(__fmul_rn(t, t), 1.f)));
+          const float sn = __fmul_rn(t, c);
+          const float tau = __fmul_rn(t, a02);
+          a00 = __fsub_rn(a00, tau);
+          a22 = __fadd_rn(a22, tau);
+          a02 = 0.f;
+          const float b01 = __fsub_rn(__fmul_rn(c, a01), __fmul_rn(sn, a12));
+          const float b12 = __fadd_rn(__fmul_rn(sn, a01), __fmul_rn(c, a12));
+          a01 = b01;
+          a12 = b12;
+        }
+        if (a12 != 0.f)
+        {
+          const float theta = __fdiv_rn(__fsub_rn(a22, a11), __fmul_rn(2.f, a12));
+          float t = __fdiv_rn(1.f, __fadd_rn(fabsf(theta), __fsqrt_rn(__fadd_rn(__fmul_rn(theta, theta), 1.f))));
+          if (theta < 0.f)
+            t = -t;
+          const float c = __fdiv_rn(1.f, __fsqrt_rn(__fadd_rn(__fmul_rn(t, t), 1.f)));
+          const float sn = __fmul_rn(t, c);
+          const float tau = __fmul_rn(t, a12);
+          a11 = __fsub_rn(a11, tau);
+          a22 = __fadd_rn(a22, tau);
+          a12 = 0.f;
+          const float b01 = __fsub_rn(__fmul_rn(c, a01), __fmul_rn(sn, a02));
+          const float b02 = __fadd_rn(__fmul_rn(sn, a01), __fmul_rn(c, a02));
+          a01 = b01;
+          a02 = b02;
+        }
+      }
+      lambda[0] = a00;
+      lambda[1] = a11;
+      lambda[2] = a22;
+    }
+
+    // Matrix3f::inverse(): cofactors times 1/det (Eigen 3.4 size-3 path), used
+    // at RefineExtremum.cpp:85.  Row-major.
+    __device__ void inverse3(const float m[9], float r[9])
+    {
+#define M_(i, j) m[3 * (i) + (j)]
+#define COF_(i, j)                                                                                 \
+  __fsub_rn(__fmul_rn(M_(((i) + 1) % 3, ((j) + 1) % 3), M_(((i) + 2) % 3, ((j) + 2) % 3)),         \
+            __fmul_rn(M_(((i) + 1) % 3, ((j) + 2) % 3), M_(((i) + 2) % 3, ((j) + 1) % 3)))
+      const float c0 = COF_(0, 0), c1 = COF_(1, 0), c2 = COF_(2, 0);
+      const float det = __fadd_rn(__fadd_rn(__fmul_rn(c0, M_(0, 0)), __fmul_rn(c1, M_(1, 0))),
+                                  __fmul_rn(c2, M_(2, 0)));
+      const float invdet = __fdiv_rn(1.f, det);
+      r[0] = __fmul_rn(c0, invdet);
+      r[1] = __fmul_rn(c1, invdet);
+      r[2] = __fmul_rn(c2, invdet);
+      r[3] = __fmul_rn(COF_(0, 1), invdet);
+      r[4] = __fmul_rn(COF_(1, 1), invdet);
+      r[5] = __fmul_rn(COF_(2, 1), invdet);
+      r[6] = __fmul_rn(COF_(0, 2), invdet);
+      r[7] = __fmul_rn(COF_(1, 2), invdet);
+      r[8] = __fmul_rn(COF_(2, 2), invdet);
+#undef COF_
+#undef M_
+    }
+
+    __global__ void __launch_bounds__(128)
+        refine_kernel(const __grid_constant__ PyramidDesc P, const ExtremaParams ep,
+                      const Candidate* __restrict__ cand, const Counters* __restrict__ counters,
+                      int cap_cand, Keypoint* __restrict__ ext_tmp, int* __restrict__ keep)
+    {
+      const int n = min(counters->n_cand, cap_cand);
+      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+      {
+        const Candidate cd = cand[i];
+        const int o = cd.so >> 8, s = cd.so & 0xff;
+        const OctaveDesc& oc = P.oct[o];
+        const Sampler I{oc.D, oc.pitch, oc.layer_stride};
+        const int n_dog = P.n_scales - 1;
+        const int type = cd.type;  // 1 or 255
+        int x = cd.x, y = cd.y;
+
+        float Dp[3] = {0.f, 0.f, 0.f};
+        float Dpp[9];
+        float hh[3] = {0.f, 0.f, 0.f};
+        float lambda[3];
+        float val = I(x, y, s);
+        bool refined_ok = true;
+
+#pragma unroll 1
+        for (int it = 0; it < ep.refine_iter; ++it)
+        {
+          if (x < ep.pad || x >= oc.w - ep.pad || y < ep.pad || y >= oc.h - ep.pad || s < 1 ||
+              s >= n_dog - 1)
+            break;
+          // gradient / hessian of the pyramid, GaussianPyramid.hpp:184-233.
+          Dp[0] = __fdiv_rn(__fsub_rn(I(x + 1, y, s), I(x - 1, y, s)), 2.f);
+          Dp[1] = __fdiv_rn(__fsub_rn(I(x, y + 1, s), I(x, y - 1, s)), 2.f);
+          Dp[2] = __fdiv_rn(__fsub_rn(I(x, y, s + 1), I(x, y, s - 1)), 2.f);
+          const float c2 = __fmul_rn(2.f, I(x, y, s));
+          Dpp[0] = __fadd_rn(__fsub_rn(I(x + 1, y, s), c2), I(x - 1, y, s));
+          Dpp[4] = __fadd_rn(__fsub_rn(I(x, y + 1, s), c2), I(x, y - 1, s));
+          Dpp[8] = __fadd_rn(__fsub_rn(I(x, y, s + 1), c2), I(x, y, s - 1));
+          Dpp[1] = Dpp[3] = __fdiv_rn(
+              __fadd_rn(__fsub_rn(__fsub_rn(I(x + 1, y + 1, s), I(x - 1, y + 1, s)), I(x + 1, y - 1, s)),
+                        I(x - 1, y - 1, s)),
+              4.f);
+          Dpp[2] = Dpp[6] = __fdiv_rn(
+              __fadd_rn(__fsub_rn(__fsub_rn(I(x + 1, y, s + 1), I(x - 1, y, s + 1)), I(x + 1, y, s - 1)),
+                        I(x - 1, y, s - 1)),
+              4.f);
+          Dpp[5] = Dpp[7] = __fdiv_rn(
+              __fadd_rn(__fsub_rn(__fsub_rn(I(x, y + 1, s + 1), I(x, y - 1, s + 1)), I(x, y + 1, s - 1)),
+                        I(x, y - 1, s - 1)),
+              4.f);
+
+          sym3_eigenvalues(Dpp, lambda);
+          const float ft = static_cast<float>(type);
+          const float lmax =
+              fmaxf(fmaxf(__fmul_rn(lambda[0], ft), __fmul_rn(lambda[1], ft)), __fmul_rn(lambda[2], ft));
+          if (lmax >= 0.f)
+          {
+            hh[0] = hh[1] = hh[2] = 0.f;
+            break;
+          }
+          float inv[9];
+          inverse3(Dpp, inv);
+#pragma unroll
+          for (int r = 0; r < 3; ++r)
+            hh[r] = __fadd_rn(__fadd_rn(__fmul_rn(-inv[3 * r + 0], Dp[0]), __fmul_rn(-inv[3 * r + 1], Dp[1])),
+                              __fmul_rn(-inv[3 * r + 2], Dp[2]));
+          if (fmaxf(fabsf(hh[0]), fabsf(hh[1])) > 1.5f)
+          {
+            refined_ok = false;  // `return false`: position and value stay as initialised
+            break;
+          }
+          if (fminf(fabsf(hh[0]), fabsf(hh[1])) > 0.6f)
+          {
+            x += hh[0] > 0.f ? 1 : -1;
+            y += hh[1] > 0.f ? 1 : -1;
+            continue;
+          }
+          break;
+        }
+
+        float px, py, pz;
+        if (!refined_ok)
+        {
+          // RefineExtremum.cpp:41-43: pos initialised to the integer slot before
+          // the loop and never updated on the early return.
+          px = static_cast<float>(cd.x);
+          py = static_cast<float>(cd.y);
+          pz = P.scale_rel[s];
+        }
+        else
+        {
+          px = static_cast<float>(x);
+          py = static_cast<float>(y);
+          pz = P.scale_rel[s];
+          const float oldval = I(x, y, s);
+          const float newval = __fadd_rn(
+              oldval,
+              __fmul_rn(0.5f, __fadd_rn(__fadd_rn(__fmul_rn(Dp[0], hh[0]), __fmul_rn(Dp[1], hh[1])),
+                                        __fmul_rn(Dp[2], hh[2]))));
+          if ((type == 1 && oldval <= newval) || (type == -1 && oldval >= newval))
+          {
+            px = __fadd_rn(px, hh[0]);
+            py = __fadd_rn(py, hh[1]);
+            // std::pow(float, float): evaluated in double and rounded, which
+            // agrees with a correctly rounded powf.
+            pz = __fmul_rn(pz, static_cast<float>(pow(static_cast<double>(P.k), static_cast<double>(hh[2]))));
+            val = newval;
+          }
+        }
+
+        Keypoint kp;
+        kp.x = px;
+        kp.y = py;
+        // OERegion(coords, scale): shape = I * std::pow(scale, -2) (Feature.hpp:78-82),
+        // a double expression narrowed to float; scale^2 is exact in double.
+        const double pz2 = static_cast<double>(pz) * static_cast<double>(pz);
+        const float a = static_cast<float>(1.0 / pz2);
+        kp.shape[0] = a;
+        kp.shape[1] = 0.f;
+        kp.shape[2] = 0.f;
+        kp.shape[3] = a;
+        kp.orientation = 0.f;
+        kp.extremum_value = val;
+        kp.type = 11;
+        kp.extremum_type = type == 1 ? 1 : -1;
+        kp.reserved = 0;
+        kp.s = s;
+        kp.o = o;
+        kp.xi = cd.x;
+        kp.yi = cd.y;
+        ext_tmp[i] = kp;
+        keep[i] = fabsf(val) < ep.extremum_thres ? 0 : 1;
+      }
+    }
+
+    __global__ void __launch_bounds__(256)
+        emit_kept_kernel(const Keypoint* __restrict__ ext_tmp, const int* __restrict__ keep,
+                         const int* __restrict__ off, const int* __restrict__ chunk_off,
+                         const Counters* __restrict__ counters, int cap_cand, Keypoint* __restrict__ ext,
+                         int cap_ext)
+    {
+      const int n = min(counters->n_cand, cap_cand);
+      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        if (keep[i])
+        {
+          const int pos = off[i] + chunk_off[i >> 10];
+          if (pos < cap_ext)
+            ext[pos] = ext_tmp[i];
+        }
+    }
+
+  }  // namespace
+
+  int launch_extrema(const PyramidDesc& P, const ExtremaParams& ep, int n_segments, int* seg_offsets,
+                     Candidate* cand, int cap_cand, Keypoint* ext_tmp, uint8_t* keep_unused, int* scratch,
+                     Keypoint* ext, int cap_ext, Counters* counters, cudaStream_t st)
+  {
+    (void) keep_unused;
+    int launches = 0;
+    const int n_s = P.n_scales - 3;
+    // row counts of all octaves are contiguous, starting at octave 0's.
+    cudaMemsetAsync(P.oct[0].row_count, 0, sizeof(int) * n_segments, st);
+    for (int o = 0; o < P.n_octaves; ++o)
+    {
+      const OctaveDesc& oc = P.oct[o];
+      dim3 grid((oc.w + 31) / 32, (oc.h + 7) / 8, n_s);
+      classify_kernel<<<grid, dim3(32, 8), 0, st>>>(oc, ep);
+      ++launches;
+    }
+    // scratch layout: [chunk offsets (1024)] [keep flags cap_cand] [flag offsets cap_cand]
+    int* chunk_off = scratch;
+    int* keep = scratch + 1024;
+    int* keep_off = keep + cap_cand;
+
+    launches += exclusive_scan(P.oct[0].row_count, seg_offsets, chunk_off, n_segments, nullptr, 0,
+                               &counters->n_cand, cap_cand, &counters->overflow, 1, st);
+    compact_rows_kernel<<<296, 256, 0, st>>>(P, n_segments, seg_offsets, chunk_off, cand, cap_cand);
+    refine_kernel<<<592, 128, 0, st>>>(P, ep, cand, counters, cap_cand, ext_tmp, keep);
+    launches += 2;
+    launches += exclusive_scan(keep, keep_off, chunk_off, 0, &counters->n_cand, cap_cand,
+                               &counters->n_ext, cap_ext, &counters->overflow, 2, st);
+    emit_kept_kernel<<<296, 256, 0, st>>>(ext_tmp, keep, keep_off, chunk_off, counters, cap_cand, ext,
+                                          cap_ext);
+    ++launches;
+    return launches;
+  }
+
+}  // namespace sb

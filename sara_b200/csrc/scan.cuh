@@ -1,0 +1,111 @@
+// Device-wide exclusive scan of an int32 array whose length may live in device
+// memory (data-dependent counts never come back to the host mid-frame).
+// Two launches: per-chunk scans (1024 items per chunk), then one block scans the
+// chunk totals.  The global offset of item i is out_off[i] + chunk_off[i >> 10].
+// Integer adds only => deterministic, order-preserving compaction.
+#pragma once
+#include "common.cuh"
+
+namespace sb {
+
+  namespace scan_detail {
+
+    // Exclusive scan of one value per thread across a 1024-thread block.
+    __device__ __forceinline__ int block_exclusive_scan_1024(int v, int* total)
+    {
+      __shared__ int warp_sums[32];
+      const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+      int inc = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1)
+      {
+        const int t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d)
+          inc += t;
+      }
+      if (lane == 31)
+        warp_sums[wid] = inc;
+      __syncthreads();
+      if (wid == 0)
+      {
+        int ws = warp_sums[lane];
+        int winc = ws;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+          const int t = __shfl_up_sync(0xffffffffu, winc, d);
+          if (lane >= d)
+            winc += t;
+        }
+        warp_sums[lane] = winc - ws;  // exclusive
+        if (lane == 31)
+          *total = winc;
+      }
+      __syncthreads();
+      const int r = warp_sums[wid] + inc - v;
+      __syncthreads();
+      return r;
+    }
+
+    static __global__ void __launch_bounds__(1024)
+        scan_chunks_kernel(const int* __restrict__ vals, int* __restrict__ out_off,
+                           int* __restrict__ chunk_tot, int n_static, const int* __restrict__ n_ptr,
+                           int n_cap)
+    {
+      __shared__ int total;
+      const int n = n_ptr ? min(*n_ptr, n_cap) : n_static;
+      const int n_chunks = (n + 1023) >> 10;
+      for (int c = blockIdx.x; c < n_chunks; c += gridDim.x)
+      {
+        const int i = (c << 10) + threadIdx.x;
+        const int v = i < n ? vals[i] : 0;
+        const int e = block_exclusive_scan_1024(v, &total);
+        if (i < n)
+          out_off[i] = e;
+        if (threadIdx.x == 0)
+          chunk_tot[c] = total;
+        __syncthreads();
+      }
+    }
+
+    static __global__ void __launch_bounds__(1024)
+        scan_totals_kernel(int* __restrict__ chunk_tot, int n_static, const int* __restrict__ n_ptr,
+                           int n_cap, int* __restrict__ total_out, int total_cap,
+                           int* __restrict__ overflow, int overflow_bit)
+    {
+      __shared__ int total;
+      const int n = n_ptr ? min(*n_ptr, n_cap) : n_static;
+      const int n_chunks = (n + 1023) >> 10;  // <= 1024
+      const int v = static_cast<int>(threadIdx.x) < n_chunks ? chunk_tot[threadIdx.x] : 0;
+      const int e = block_exclusive_scan_1024(v, &total);
+      if (static_cast<int>(threadIdx.x) < n_chunks)
+        chunk_tot[threadIdx.x] = e;
+      if (threadIdx.x == 0)
+      {
+        if (total > total_cap)
+          atomicOr(overflow, overflow_bit);
+        *total_out = total;  // the true count; consumers clamp to their capacity
+      }
+    }
+
+  }  // namespace scan_detail
+
+  // Returns the number of kernels launched.
+  static inline int exclusive_scan(const int* vals, int* out_off, int* chunk_off, int n_static,
+                                   const int* n_ptr, int n_cap, int* total_out, int total_cap,
+                                   int* overflow, int overflow_bit, cudaStream_t st)
+  {
+    const int max_n = n_ptr ? n_cap : n_static;
+    int grid = (max_n + 1023) >> 10;
+    if (grid < 1)
+      grid = 1;
+    if (grid > 1024)
+      grid = 1024;
+    scan_detail::scan_chunks_kernel<<<grid, 1024, 0, st>>>(vals, out_off, chunk_off, n_static, n_ptr,
+                                                           n_cap);
+    scan_detail::scan_totals_kernel<<<1, 1024, 0, st>>>(chunk_off, n_static, n_ptr, n_cap, total_out,
+                                                        total_cap, overflow, overflow_bit);
+    return 2;
+  }
+
+}  // namespace sb

@@ -1,0 +1,104 @@
+"""Shared comparison helpers: CUDA path (through the C ABI) vs the CPU oracle.
+
+Tolerances (written here so the tests state them):
+  * Gaussian / DoG layers ................ bit-identical (memcmp)
+  * extrema (xi, yi, s, o, type) ......... identical ordered sequence
+  * refined x, y, extremum value ......... bit-identical (only +,-,*,/,sqrt involved)
+  * refined sigma / shape ................ |rel| <= 1e-6 (powf on the CPU vs pow->float)
+  * orientation .......................... same count per extremum for >= 99.9 %;
+                                           |dtheta| <= 1e-3 rad on matched keypoints
+  * descriptors (0..255 scale) ........... ||d_gpu - d_cpu||_2 <= 1e-3 ||d_cpu||_2 + 0.05
+                                           for >= 99.9 % of matched keypoints
+"""
+from __future__ import annotations
+
+import numpy as np
+
+DESC_REL, DESC_ABS, DESC_FRACTION = 1e-3, 0.05, 0.999
+ORI_TOL, ORI_FRACTION = 1e-3, 0.999
+
+
+def assert_pyramids_identical(ctx, ref, slot=0):
+    assert ctx.num_octaves(slot) == ref.num_octaves
+    assert ctx.num_scales(slot) == ref.num_scales
+    for o in range(ref.num_octaves):
+        assert ctx.layer_size(o, slot) == ref.layer_size(o)
+        assert ctx.octave_scaling_factor(o, slot) == ref.octave_scaling(o)
+        for s in range(ref.num_scales):
+            g, r = ctx.gaussian_layer(s, o, slot), ref.gaussian(s, o)
+            assert g.tobytes() == r.tobytes(), f"G({s},{o}) differs: max |d| = {np.abs(g - r).max()}"
+        for s in range(ref.num_scales - 1):
+            g, r = ctx.dog_layer(s, o, slot), ref.dog(s, o)
+            assert g.tobytes() == r.tobytes(), f"D({s},{o}) differs: max |d| = {np.abs(g - r).max()}"
+
+
+def assert_extrema_identical(e_gpu: np.ndarray, e_ref: np.ndarray):
+    assert len(e_gpu) == len(e_ref), f"extrema count {len(e_gpu)} vs {len(e_ref)}"
+    for f in ("xi", "yi", "s", "o", "extremum_type", "type"):
+        assert np.array_equal(e_gpu[f], e_ref[f]), f"extrema field {f} differs"
+    for f in ("x", "y", "extremum_value"):
+        assert e_gpu[f].tobytes() == e_ref[f].tobytes(), f"extrema field {f} is not bit-identical"
+    if len(e_ref):
+        rel = np.abs(e_gpu["shape"] - e_ref["shape"]) / np.maximum(np.abs(e_ref["shape"]), 1e-30)
+        assert rel.max() <= 1e-6, f"shape matrix rel err {rel.max()}"
+
+
+def _group_key(k):
+    return np.stack([k["o"], k["s"], k["yi"], k["xi"]], axis=1)
+
+
+def match_oriented(k_gpu: np.ndarray, k_ref: np.ndarray):
+    """Pairs keypoints of the two ordered lists extremum by extremum.  Returns
+    (idx_gpu, idx_ref, n_extrema_with_count_mismatch, n_extrema)."""
+    def groups(k):
+        key = _group_key(k)
+        out, start = [], 0
+        for i in range(1, len(k) + 1):
+            if i == len(k) or not np.array_equal(key[i], key[start]):
+                out.append((tuple(key[start]), start, i))
+                start = i
+        return out
+
+    gg, gr = groups(k_gpu), groups(k_ref)
+    dr = {g[0]: g for g in gr}
+    dg = {g[0]: g for g in gg}
+    ig, ir, bad = [], [], 0
+    for key in set(dr) | set(dg):
+        a, b = dg.get(key), dr.get(key)
+        if a is None or b is None or (a[2] - a[1]) != (b[2] - b[1]):
+            bad += 1
+            continue
+        ig.extend(range(a[1], a[2]))
+        ir.extend(range(b[1], b[2]))
+    order = np.argsort(ir)
+    return np.asarray(ig, int)[order], np.asarray(ir, int)[order], bad, len(set(dr) | set(dg))
+
+
+def compare_keypoints(k_gpu, d_gpu, k_ref, d_ref, scaling=None):
+    """Returns a dict of statistics and asserts the tolerances above."""
+    ig, ir, bad, n_ext = match_oriented(k_gpu, k_ref)
+    stats = {"n_gpu": len(k_gpu), "n_ref": len(k_ref), "extrema": n_ext, "count_mismatch": bad}
+    if n_ext:
+        assert bad <= max(1, int((1 - ORI_FRACTION) * n_ext)), f"{bad}/{n_ext} extrema differ in orientation count"
+    if len(ir) == 0:
+        return stats
+    a, b = k_gpu[ig], k_ref[ir]
+    dth = np.abs(a["orientation"] - b["orientation"])
+    dth = np.minimum(dth, 2 * np.pi - dth)
+    ok_ori = dth <= ORI_TOL
+    stats["ori_max"] = float(dth.max())
+    stats["ori_bad"] = int((~ok_ori).sum())
+    assert ok_ori.mean() >= ORI_FRACTION, f"{(~ok_ori).sum()}/{len(ok_ori)} orientations off by > {ORI_TOL}"
+    assert np.allclose(a["x"], b["x"], rtol=1e-6, atol=0) and np.allclose(a["y"], b["y"], rtol=1e-6, atol=0)
+    da, db = d_gpu[ig].astype(np.float64), d_ref[ir].astype(np.float64)
+    both_nan = np.isnan(da).any(1) & np.isnan(db).any(1)
+    err = np.linalg.norm(np.nan_to_num(da - db), axis=1)
+    tol = DESC_REL * np.linalg.norm(np.nan_to_num(db), axis=1) + DESC_ABS
+    ok = (err <= tol) | both_nan
+    # keypoints whose orientation itself differs are excluded from the descriptor statistic
+    ok_desc = ok | ~ok_ori
+    stats["desc_err_max"] = float(err.max())
+    stats["desc_err_median"] = float(np.median(err))
+    stats["desc_bad"] = int((~ok_desc).sum())
+    assert ok_desc.mean() >= DESC_FRACTION, f"{(~ok_desc).sum()}/{len(ok_desc)} descriptors beyond tolerance (max {err.max()})"
+    return stats
