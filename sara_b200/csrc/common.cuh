@@ -78,8 +78,9 @@ namespace sb {
 
   // Fused octave kernel for the default SIFT schedule (pyramid_fused.cu).
   bool fused_octave_supported(const Taps* taps, int n_scales);
-  void launch_fused_octave(const OctaveDesc& oct, const OctaveDesc* next, int downscale_index,
-                           const Taps* taps, int n_scales, cudaStream_t st);
+  // Returns the number of kernels launched, or -1 if the launch could not be set up.
+  int launch_fused_octave(const OctaveDesc& oct, const OctaveDesc* next, int downscale_index,
+                          const Taps* taps, int n_scales, cudaStream_t st);
 
   struct ExtremaParams
   {

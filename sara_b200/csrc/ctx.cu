@@ -379,8 +379,10 @@ namespace {
         const OctaveDesc* next = o + 1 < P.n_octaves ? &P.oct[o + 1] : nullptr;
         if (fused)
         {
-          launch_fused_octave(oc, next, S.downscale_index, S.stage_taps.data(), P.n_scales, st);
-          ++S.pyramid_launches;
+          const int n = launch_fused_octave(oc, next, S.downscale_index, S.stage_taps.data(), P.n_scales, st);
+          if (n < 0)
+            return fail(ctx, SARA_B200_ERR_CUDA, "fused octave kernel could not be launched (tensor map / attributes)");
+          S.pyramid_launches += n;
           continue;
         }
         for (int s = 1; s < P.n_scales; ++s)

@@ -72,6 +72,39 @@ def test_pyramid_bit_exact(ctx, name, w, h, fo):
     assert_pyramids_identical(ctx, ref)
 
 
+@pytest.fixture(scope="module")
+def wide_ctx():
+    c = sb.SiftContext(2048, 1200, max_keypoints=65536)
+    yield c
+    c.close()
+
+
+# Sizes that exercise the fused octave kernel's strips and segments: several strips
+# of both tile widths, odd widths/heights (ragged last strip, straddling column
+# pair), segment seams, and images narrower than the cascade halo.
+@pytest.mark.parametrize("w,h", [(1300, 420), (1281, 333), (2000, 300), (1025, 1100), (1920, 1080),
+                                 (129, 700), (257, 97), (90, 1000), (1000, 41), (31, 31)])
+def test_fused_octave_bit_exact(wide_ctx, w, h):
+    img = S.tex(w, h, 7)
+    p_gpu, p_ref = _pp(0)
+    ref = O.compute_dog_extrema(img, p_ref)
+    wide_ctx.pyramid_enqueue(0, img, p_gpu)
+    wide_ctx.wait(0)
+    assert_pyramids_identical(wide_ctx, ref)
+
+
+def test_fused_octave_noise_and_negative_values(wide_ctx):
+    # white noise (every tap matters) and signed data (signed zeros / cancellation)
+    rng = np.random.default_rng(5)
+    for img in (rng.random((300, 1111), dtype=np.float32),
+                (rng.standard_normal((257, 640)) * 3).astype(np.float32)):
+        p_gpu, p_ref = _pp(0)
+        ref = O.compute_dog_extrema(img, p_ref)
+        wide_ctx.pyramid_enqueue(0, img, p_gpu)
+        wide_ctx.wait(0)
+        assert_pyramids_identical(wide_ctx, ref)
+
+
 def test_pyramid_other_schedules(ctx):
     img = S.tex(256, 192, 5)
     for kw in (dict(scale_count_per_octave=5, scale_geometric_factor=float(np.float32(2.0) ** np.float32(0.5))),
