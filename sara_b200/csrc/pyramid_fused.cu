@@ -41,35 +41,38 @@ namespace sb {
 
     typedef unsigned long long u64;
 
-    constexpr int NT = 384;  // threads per CTA
-    constexpr int NWARP = NT / 32;
+    constexpr int NT = 640;  // threads per CTA (20 warps)
     constexpr int HALO = 41;  // 5 + 6 + 8 + 10 + 12
     constexpr int TMA_SKEW = 3;  // (HALO + TMA_SKEW) % 4 == 0
+    constexpr int ROWTAB = 40;   // ring-row table entries per stage
 
     __host__ __device__ constexpr int K_(int s) { return s == 1 ? 11 : s == 2 ? 13 : s == 3 ? 17 : s == 4 ? 21 : 25; }
     __host__ __device__ constexpr int C_(int s) { return K_(s) / 2; }
-    // cumulative radius of stages 1..s
-    __host__ __device__ constexpr int CS_(int s) { return s <= 0 ? 0 : CS_(s - 1) + C_(s); }
+    // cumulative radius of stages 1..s (closed form: a recursive constexpr called with a loop
+    // variable is NOT folded by nvcc and becomes a real recursive device call)
+    __host__ __device__ constexpr int CS_(int s) { return s <= 0 ? 0 : s == 1 ? 5 : s == 2 ? 11 : s == 3 ? 19 : s == 4 ? 29 : 41; }
     // halo still needed after stage s (s = 0: the input)
     __host__ __device__ constexpr int H_(int s) { return HALO - CS_(s); }
-    // 8-row blocks kept in the ring of stage s: the window of a column pass spans
+    // 8-row blocks kept in the ring of stage s: the windows of a column pass span
     // rows [a - 2c, a + 7] of the block that starts at row a.
     __host__ __device__ constexpr int NB_(int s) { return (2 * C_(s) + 7) / 8 + 1; }
+    __host__ __device__ constexpr int round_to(int v, int mod, int rem) { return v + ((rem - v % mod) + mod) % mod; }
 
     template <int TX>
     struct Cfg
     {
       __host__ __device__ static constexpr int W(int s) { return TX + 2 * H_(s); }
-      __host__ __device__ static constexpr int NCH(int s) { return (W(s) + 7) / 8; }  // 8-column chunks of a row pass
-      __host__ __device__ static constexpr int PR(int s) { return 8 * NCH(s); }       // ring pitch (floats)
-      // Block of G(s) rows handed to stage s + 1, row-pair interleaved: [4][P][2].
-      // P = 2 (mod 16) makes the float4 window loads of a row pass conflict free.
+      __host__ __device__ static constexpr int NCH4(int s) { return (W(s) + 3) / 4; }  // 4-column chunks of a row pass
+      // Ring pitch (floats).  = 8 (mod 16): the two float4 stores of a row-pass item are conflict free.
+      __host__ __device__ static constexpr int PR(int s) { return round_to(4 * NCH4(s), 16, 8); }
+      // Block of G(s) rows handed to stage s + 1, row-pair interleaved: [4][P][2] floats.
+      // The row pass of stage s + 1 reads positions up to 4 NCH4 + K + 7; P = 2 (mod 4) makes its
+      // 16-byte window loads conflict free.
       __host__ __device__ static constexpr int P(int s)
       {
-        int need = 8 * NCH(s + 1) + K_(s + 1);
+        int need = 4 * NCH4(s + 1) + K_(s + 1) + 8;
         need = need < W(s) ? W(s) : need;
-        need = (need + 1) & ~1;
-        return need + ((2 - need % 16) + 16) % 16;
+        return round_to(need, 4, 2);
       }
       // TMA box width.  The x coordinate of a box must be 16-byte aligned (a misaligned one
       // raises "illegal instruction", profiles/microbench/tma_probe.cu), so the two boxes of a
@@ -77,13 +80,38 @@ namespace sb {
       __host__ __device__ static constexpr int BOXW() { return ((W(0) + TMA_SKEW + 1) / 2 + 3) & ~3; }
       // shared memory map (float offsets)
       __host__ __device__ static constexpr int inraw_floats() { return 2 * 2 * 8 * BOXW(); }
-      __host__ __device__ static constexpr int off_out(int s) { return s == 0 ? inraw_floats() : off_out(s - 1) + 8 * P(s - 1); }
-      __host__ __device__ static constexpr int off_ring(int s) { return s == 1 ? off_out(4) + 8 * P(4) : off_ring(s - 1) + NB_(s - 1) * 8 * PR(s - 1); }
-      __host__ __device__ static constexpr int total_floats() { return off_ring(5) + NB_(5) * 8 * PR(5); }
+      __host__ __device__ static constexpr int off_out(int s)
+      {
+        int o = inraw_floats();
+        for (int i = 0; i < s; ++i)
+          o += 8 * P(i);
+        return o;
+      }
+      __host__ __device__ static constexpr int off_ring(int s)
+      {
+        int o = off_out(5);
+        for (int i = 1; i < s; ++i)
+          o += NB_(i) * 8 * PR(i);
+        return o;
+      }
+      __host__ __device__ static constexpr int off_rowtab() { return off_ring(6); }
+      __host__ __device__ static constexpr int total_floats() { return off_rowtab() + 5 * ROWTAB; }
       __host__ __device__ static constexpr int smem_bytes() { return total_floats() * 4 + 64; }
       // warp items
-      __host__ __device__ static constexpr int NWA(int s) { return (NCH(s) + 7) / 8; }   // row pass: 4 row pairs x 8 chunks
-      __host__ __device__ static constexpr int NWB(int s) { return (W(s) / 2 + 31) / 32; }  // column pass: 32 column pairs
+      __host__ __device__ static constexpr int NWA(int s) { return (NCH4(s) + 7) / 8; }          // row pass: 4 row pairs x 8 chunks
+      __host__ __device__ static constexpr int NWB(int s) { return 2 * ((W(s) / 2 + 31) / 32); }  // column pass: 32 column pairs x 4 rows
+    };
+
+    // One cascade stage as the kernel sees it (uniform values, read from the constant bank).
+    struct StageDesc
+    {
+      int K, c, depth;      // taps, radius, ring rows (8 * NB)
+      int W, HS, HP;        // width of the stage's region; halo after / before the stage
+      int CSP, CSS;         // cumulative radius before / after the stage
+      int off_in, P_in;     // block of G(s-1): float offset, pitch (x positions)
+      int off_ring, PR;     // ring of row-filtered rows
+      int off_out, P_out;   // block of G(s) for the next stage (unused for s = 5)
+      int NCH4, NWA, NWB;
     };
 
     struct Params
@@ -95,7 +123,8 @@ namespace sb {
       int nw, nh, npitch;
       int hy;  // rows per segment
       float one;
-      float taps[5][25];
+      StageDesc sd[6];  // [1..5]
+      float taps[6][28];  // [1..5][K]
     };
 
     struct Ctl
@@ -163,77 +192,129 @@ namespace sb {
           : "memory");
     }
 
-    // ---- row pass of stage S: block of G(S-1) (interleaved row pairs) -> ring of stage S ----
-    template <int TX, int S>
-    __device__ __forceinline__ void row_item(float* sm, const Params& prm, const Ctl& ctl, int t, int wi, int lane)
+    // One block of NTAP consecutive taps on a register window: acc[q] += w[q + jj] * k[jb + jj].
+    template <int NTAP>
+    __device__ __forceinline__ void tap_block(u64 (&acc)[4], const u64 (&w)[12], const float* __restrict__ taps, int jb,
+                                              u64 one)
     {
-      using C = Cfg<TX>;
-      constexpr int K = K_(S);
-      const int rp = lane & 3, ch = wi * 8 + (lane >> 2);
-      if (ch >= C::NCH(S))
-        return;
-      const int u = t - (S - 1);
-      const int a = ctl.Y + 8 * u - CS_(S - 1);
-      const int ya = a + 2 * rp;
-      const int lo = max(0, ctl.y0 - H_(S - 1)), hi = min(prm.h, ctl.y1 + H_(S - 1));
-      if (ya + 1 < lo || ya >= hi)
-        return;
-      const float* in = sm + C::off_out(S - 1) + (rp * C::P(S - 1) + 8 * ch) * 2;
-      constexpr int NV = (K + 7 + 1) / 2;  // 16-byte loads: two x positions (both rows) each
-      u64 win[2 * NV];
 #pragma unroll
-      for (int m = 0; m < NV; ++m)
+      for (int jj = 0; jj < NTAP; ++jj)
       {
-        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(in + 4 * m);
-        win[2 * m] = v.x;
-        win[2 * m + 1] = v.y;
+        const float k = taps[jb + jj];
+        const u64 kk = pack2(k, k);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          acc[q] = add2(acc[q], mul2(w[q + jj], kk), one);
       }
-      const u64 one = pack2(prm.one, prm.one);
-      u64 acc[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q)
-        acc[q] = 0ull;
-#pragma unroll
-      for (int j = 0; j < K; ++j)
-      {
-        const u64 kk = pack2(prm.taps[S - 1][j], prm.taps[S - 1][j]);
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-          acc[q] = add2(acc[q], mul2(win[q + j], kk), one);
-      }
-      const int slot = (u + 8 * NB_(S)) % NB_(S);
-      float* out = sm + C::off_ring(S) + (slot * 8 + 2 * rp) * C::PR(S) + 8 * ch;
-      *reinterpret_cast<float4*>(out) = make_float4(lo2(acc[0]), lo2(acc[1]), lo2(acc[2]), lo2(acc[3]));
-      *reinterpret_cast<float4*>(out + 4) = make_float4(lo2(acc[4]), lo2(acc[5]), lo2(acc[6]), lo2(acc[7]));
-      *reinterpret_cast<float4*>(out + C::PR(S)) = make_float4(hi2(acc[0]), hi2(acc[1]), hi2(acc[2]), hi2(acc[3]));
-      *reinterpret_cast<float4*>(out + C::PR(S) + 4) = make_float4(hi2(acc[4]), hi2(acc[5]), hi2(acc[6]), hi2(acc[7]));
     }
 
-    // ---- column pass of stage S --------------------------------------------------------
-    // One lane = two adjacent columns (packed), 8 output rows [b, b + 8).
-    template <int TX, int S>
-    __device__ __forceinline__ void col_item(float* sm, const Params& prm, const Ctl& ctl, int t, int wi, int lane)
+    // ---- row pass of stage s: block of G(s-1) (interleaved row pairs) -> ring of stage s ----
+    // Warp item = 4 row pairs x 8 chunks of 4 columns; a lane filters 4 columns of 2 rows
+    // (the two rows ride in the two halves of the f32x2 registers).
+    __device__ __forceinline__ void row_item(float* sm, const Params& prm, const Ctl& ctl, int s, int t, int wi, int lane)
     {
-      using C = Cfg<TX>;
-      constexpr int K = K_(S), c = C_(S), NB = NB_(S), PR = C::PR(S);
-      const int u = t - (S - 1);
-      const int a = ctl.Y + 8 * u - CS_(S - 1);
-      const int b = a - c;
-      const int i = 2 * (wi * 32 + lane);     // local column of the low lane
-      const int xs = ctl.x0 - H_(S);          // absolute x of local column 0 (even)
-      const int x = xs + i;
-      const int w = prm.w, h = prm.h;
-      const bool active = i < C::W(S) && x >= 0 && x < w;
-      const bool central = active && i >= H_(S) && i < H_(S) + TX;
-      const bool pair_ok = x + 1 < w;
+      const StageDesc& sd = prm.sd[s];
+      // quarter-warps hold 4 chunks x 2 row pairs: conflict-free 16-byte loads and stores
+      const int rp = ((lane >> 2) & 1) | ((lane >> 3) & 2);
+      const int ch = wi * 8 + ((lane & 3) | ((lane >> 1) & 4));
+      if (ch >= sd.NCH4)
+        return;
+      const int u = t - (s - 1);
+      const int a = ctl.Y + 8 * u - sd.CSP;
+      const int ya = a + 2 * rp;
+      const int lo = max(0, ctl.y0 - sd.HP), hi = min(prm.h, ctl.y1 + sd.HP);
+      if (ya + 1 < lo || ya >= hi)
+        return;
+      const int K = sd.K;
+      const float* taps = prm.taps[s];
+      const ulonglong2* in = reinterpret_cast<const ulonglong2*>(sm + sd.off_in + (rp * sd.P_in + 4 * ch) * 2);
+      u64 w[12];
+#pragma unroll
+      for (int m = 0; m < 6; ++m)
+      {
+        const ulonglong2 v = in[m];
+        w[2 * m] = v.x;
+        w[2 * m + 1] = v.y;
+      }
+      const u64 one = pack2(prm.one, prm.one);
+      u64 acc[4] = {0ull, 0ull, 0ull, 0ull};
+      int jb = 0;
+#pragma unroll 1
+      while (jb + 8 <= K)
+      {
+        tap_block<8>(acc, w, taps, jb, one);
+        jb += 8;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          w[q] = w[q + 8];
+        if (K - jb > 1)
+        {
+#pragma unroll
+          for (int m = 0; m < 4; ++m)
+          {
+            const ulonglong2 v = in[jb / 2 + 2 + m];  // positions jb + 4 + 2m, jb + 5 + 2m
+            w[4 + 2 * m] = v.x;
+            w[5 + 2 * m] = v.y;
+          }
+        }
+      }
+      const int rem = K - jb;  // 1, 3 or 5
+      tap_block<1>(acc, w, taps, jb, one);
+      if (rem >= 3)
+      {
+        const u64(&w1)[12] = w;  // taps jb + 1, jb + 2
+        const float k1 = taps[jb + 1], k2 = taps[jb + 2];
+        const u64 kk1 = pack2(k1, k1), kk2 = pack2(k2, k2);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          acc[q] = add2(acc[q], mul2(w1[q + 1], kk1), one);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          acc[q] = add2(acc[q], mul2(w1[q + 2], kk2), one);
+        if (rem >= 5)
+        {
+          const float k3 = taps[jb + 3], k4 = taps[jb + 4];
+          const u64 kk3 = pack2(k3, k3), kk4 = pack2(k4, k4);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            acc[q] = add2(acc[q], mul2(w1[q + 3], kk3), one);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            acc[q] = add2(acc[q], mul2(w1[q + 4], kk4), one);
+        }
+      }
+      const int slot = (u + 48) % (sd.depth >> 3);  // 48: multiple of both ring sizes (3 and 4 blocks)
+      float* out = sm + sd.off_ring + (slot * 8 + 2 * rp) * sd.PR + 4 * ch;
+      *reinterpret_cast<float4*>(out) = make_float4(lo2(acc[0]), lo2(acc[1]), lo2(acc[2]), lo2(acc[3]));
+      *reinterpret_cast<float4*>(out + sd.PR) = make_float4(hi2(acc[0]), hi2(acc[1]), hi2(acc[2]), hi2(acc[3]));
+    }
 
-      // G(S-1) for the D epilogue: issued first, consumed last.
-      float2 prev[8];
+    // ---- column pass of stage s --------------------------------------------------------
+    // Warp item = 32 column pairs x 4 output rows [b + 4 half, +4); a lane owns two adjacent
+    // columns (the halves of the f32x2 registers).  Window rows come through the ring-row table
+    // (clamped to the image and wrapped around the ring), so borders need no special path.
+    __device__ __forceinline__ void col_item(float* sm, const Params& prm, const Ctl& ctl, int s, int t, int wi, int lane)
+    {
+      const StageDesc& sd = prm.sd[s];
+      const int half = wi & 1, grp = wi >> 1;
+      const int K = sd.K;
+      const int u = t - (s - 1);
+      const int b = ctl.Y + 8 * u - sd.CSS + 4 * half;  // first output row of this item
+      const int i = 2 * (grp * 32 + lane);                 // local column of the low lane
+      const int xs = ctl.x0 - sd.HS;                       // absolute x of local column 0 (even)
+      const int x = xs + i;
+      const int w_img = prm.w;
+      const bool active = i < sd.W && x >= 0 && x < w_img;
+      const bool central = active && i >= sd.HS && i < sd.W - sd.HS;
+      const bool pair_ok = x + 1 < w_img;
+
+      // G(s-1) for the D epilogue: issued first, consumed last.
+      float2 prev[4];
       if (central)
       {
-        const float* gp = prm.G + static_cast<size_t>(S - 1) * prm.layer_stride;
+        const float* gp = prm.G + static_cast<size_t>(s - 1) * prm.layer_stride;
 #pragma unroll
-        for (int r = 0; r < 8; ++r)
+        for (int r = 0; r < 4; ++r)
         {
           const int y = b + r;
           prev[r] = make_float2(0.f, 0.f);
@@ -248,120 +329,121 @@ namespace sb {
         }
       }
 
-      u64 acc[8];
-#pragma unroll
-      for (int r = 0; r < 8; ++r)
-        acc[r] = 0ull;
-      const float* ring = sm + C::off_ring(S) + i;
-      const u64 one = pack2(prm.one, prm.one);
-      const bool fast = b - c >= 0 && b + 7 + c <= h - 1;  // no row of the window needs clamping
+      u64 acc[4] = {0ull, 0ull, 0ull, 0ull};
       if (active)
       {
-        if (fast)
+        const float* taps = prm.taps[s];
+        const float* ring = sm + sd.off_ring + i;
+        const int* rowtab = reinterpret_cast<const int*>(sm + prm.sd[0].off_ring) + (s - 1) * ROWTAB + 4 * half;
+        const u64 one = pack2(prm.one, prm.one);
+        u64 w[12];
+#pragma unroll
+        for (int n = 0; n < 12; ++n)
+          w[n] = *reinterpret_cast<const u64*>(ring + rowtab[n]);
+        int jb = 0;
+#pragma unroll 1
+        while (jb + 8 <= K)
         {
-          u64 win[K + 7];
-          int base[NB];
+          tap_block<8>(acc, w, taps, jb, one);
+          jb += 8;
 #pragma unroll
-          for (int e = 0; e < NB; ++e)  // base[e]: ring block holding rows of block u - (NB - 1) + e
-            base[e] = ((u - (NB - 1) + e + 8 * NB) % NB) * 8 * PR;
-#pragma unroll
-          for (int q = 0; q < K + 7; ++q)
+          for (int q = 0; q < 4; ++q)
+            w[q] = w[q + 8];
+          if (K - jb > 1)
           {
-            const int rel = q - 2 * c;                       // row relative to the current block start
-            const int blk = (rel + 8 * NB) / 8 - NB;         // floor(rel / 8), in [-(NB - 1), 0]
-            const int rin = rel - 8 * blk;
-            win[q] = *reinterpret_cast<const u64*>(ring + base[blk + NB - 1] + rin * PR);
-          }
 #pragma unroll
-          for (int j = 0; j < K; ++j)
-          {
-            const u64 kk = pack2(prm.taps[S - 1][j], prm.taps[S - 1][j]);
-#pragma unroll
-            for (int r = 0; r < 8; ++r)
-              acc[r] = add2(acc[r], mul2(win[r + j], kk), one);
+            for (int n = 4; n < 12; ++n)
+              w[n] = *reinterpret_cast<const u64*>(ring + rowtab[jb + n]);
           }
         }
-        else
+        const int rem = K - jb;
+        tap_block<1>(acc, w, taps, jb, one);
+        if (rem >= 3)
         {
-          // Border steps: rows of the window are clamped to the image
-          // (LinearFiltering.hpp:137-142).  Same arithmetic, compact code.
-          const int origin = ctl.Y - CS_(S - 1) - 64 * NB;  // row of ring block 0, shifted to keep the modulo positive
-#pragma unroll 1
-          for (int j = 0; j < K; ++j)
-          {
-            const u64 kk = pack2(prm.taps[S - 1][j], prm.taps[S - 1][j]);
+          const float k1 = taps[jb + 1], k2 = taps[jb + 2];
+          const u64 kk1 = pack2(k1, k1), kk2 = pack2(k2, k2);
 #pragma unroll
-            for (int r = 0; r < 8; ++r)
-            {
-              const int yq = min(max(b + r - c + j, 0), h - 1);
-              const int rr = (yq - origin) % (8 * NB);
-              const u64 v = *reinterpret_cast<const u64*>(ring + rr * PR);
-              acc[r] = add2(acc[r], mul2(v, kk), one);
-            }
+          for (int q = 0; q < 4; ++q)
+            acc[q] = add2(acc[q], mul2(w[q + 1], kk1), one);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            acc[q] = add2(acc[q], mul2(w[q + 2], kk2), one);
+          if (rem >= 5)
+          {
+            const float k3 = taps[jb + 3], k4 = taps[jb + 4];
+            const u64 kk3 = pack2(k3, k3), kk4 = pack2(k4, k4);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              acc[q] = add2(acc[q], mul2(w[q + 3], kk3), one);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              acc[q] = add2(acc[q], mul2(w[q + 4], kk4), one);
           }
         }
       }
 
-      // ---- block of G(S) for the next stage (row-pair interleaved) ----
-      if (S < 5)
+      // ---- block of G(s) for the next stage (row-pair interleaved) ----
+      if (s < 5)
       {
-        float* out = sm + C::off_out(S);
+        float* out = sm + sd.off_out;
+        const int P_out = sd.P_out;
         if (active)
         {
 #pragma unroll
-          for (int rp = 0; rp < 4; ++rp)
-            *reinterpret_cast<float4*>(out + (rp * C::P(S) + i) * 2) =
-                make_float4(lo2(acc[2 * rp]), lo2(acc[2 * rp + 1]), hi2(acc[2 * rp]), hi2(acc[2 * rp + 1]));
+          for (int e = 0; e < 2; ++e)
+            *reinterpret_cast<float4*>(out + ((2 * half + e) * P_out + i) * 2) =
+                make_float4(lo2(acc[2 * e]), lo2(acc[2 * e + 1]), hi2(acc[2 * e]), hi2(acc[2 * e + 1]));
         }
-        // Replicate the border columns over the out-of-image part of the block.
+        // Replicate the border columns over the out-of-image part of the block
+        // (LinearFiltering.hpp:95-100 at the next stage): warp-shuffle broadcast.
         const int iL = -xs;              // local column of x = 0
-        const int iR = w - xs;           // local column of x = w (first one outside)
-        const bool left = iL > 0 && (iL >> 6) == wi;                       // this warp item holds x = 0
-        const int xr = (w - 1) & ~1;                                       // low lane of the pair holding x = w - 1
-        const bool right = iR < C::P(S) && xr - xs >= 0 && ((xr - xs) >> 6) == wi;
+        const int iR = w_img - xs;       // local column of x = w (first one outside)
+        const bool left = iL > 0 && (iL >> 6) == grp;                   // this warp item holds x = 0
+        const int xr = (w_img - 1) & ~1;                                // low lane of the pair holding x = w - 1
+        const bool right = iR < P_out && xr - xs >= 0 && ((xr - xs) >> 6) == grp;
         if (left || right)  // warp-uniform
         {
           __syncwarp();
           if (left)
           {
             const int src = (iL >> 1) & 31;
-            u64 v[4];
+            u64 v[2];
 #pragma unroll
-            for (int rp = 0; rp < 4; ++rp)
-              v[rp] = pack2(__shfl_sync(0xffffffffu, lo2(acc[2 * rp]), src),
-                            __shfl_sync(0xffffffffu, lo2(acc[2 * rp + 1]), src));
+            for (int e = 0; e < 2; ++e)
+              v[e] = pack2(__shfl_sync(0xffffffffu, lo2(acc[2 * e]), src),
+                           __shfl_sync(0xffffffffu, lo2(acc[2 * e + 1]), src));
             for (int ii = lane; ii < iL; ii += 32)
 #pragma unroll
-              for (int rp = 0; rp < 4; ++rp)
-                *reinterpret_cast<u64*>(out + (rp * C::P(S) + ii) * 2) = v[rp];
+              for (int e = 0; e < 2; ++e)
+                *reinterpret_cast<u64*>(out + ((2 * half + e) * P_out + ii) * 2) = v[e];
           }
           if (right)
           {
             const int src = ((xr - xs) >> 1) & 31;
-            const bool odd = (w & 1) != 0;  // x = w - 1 is the low lane of its pair
-            u64 v[4];
+            const bool odd = (w_img & 1) != 0;  // x = w - 1 is the low lane of its pair
+            u64 v[2];
 #pragma unroll
-            for (int rp = 0; rp < 4; ++rp)
+            for (int e = 0; e < 2; ++e)
             {
-              const float e0 = odd ? lo2(acc[2 * rp]) : hi2(acc[2 * rp]);
-              const float e1 = odd ? lo2(acc[2 * rp + 1]) : hi2(acc[2 * rp + 1]);
-              v[rp] = pack2(__shfl_sync(0xffffffffu, e0, src), __shfl_sync(0xffffffffu, e1, src));
+              const float e0 = odd ? lo2(acc[2 * e]) : hi2(acc[2 * e]);
+              const float e1 = odd ? lo2(acc[2 * e + 1]) : hi2(acc[2 * e + 1]);
+              v[e] = pack2(__shfl_sync(0xffffffffu, e0, src), __shfl_sync(0xffffffffu, e1, src));
             }
-            for (int ii = iR + lane; ii < C::P(S); ii += 32)
+            for (int ii = iR + lane; ii < P_out; ii += 32)
 #pragma unroll
-              for (int rp = 0; rp < 4; ++rp)
-                *reinterpret_cast<u64*>(out + (rp * C::P(S) + ii) * 2) = v[rp];
+              for (int e = 0; e < 2; ++e)
+                *reinterpret_cast<u64*>(out + ((2 * half + e) * P_out + ii) * 2) = v[e];
           }
         }
       }
 
-      // ---- global results: G(S), D(S-1), base of the next octave ----
+      // ---- global results: G(s), D(s-1), base of the next octave ----
       if (central)
       {
-        float* gs = prm.G + static_cast<size_t>(S) * prm.layer_stride;
-        float* ds = prm.D + static_cast<size_t>(S - 1) * prm.layer_stride;
+        float* gs = prm.G + static_cast<size_t>(s) * prm.layer_stride;
+        float* ds = prm.D + static_cast<size_t>(s - 1) * prm.layer_stride;
 #pragma unroll
-        for (int r = 0; r < 8; ++r)
+        for (int r = 0; r < 4; ++r)
         {
           const int y = b + r;
           if (y < ctl.y0 || y >= ctl.y1)
@@ -378,7 +460,7 @@ namespace sb {
             gs[o] = g0;
             ds[o] = __fsub_rn(g0, prev[r].x);
           }
-          if (S == 2 && prm.nextG != nullptr && (y & 1) == 0)
+          if (s == 2 && prm.nextG != nullptr && (y & 1) == 0)
           {
             const int xx = x >> 1, yy = y >> 1;
             if (xx < prm.nw && yy < prm.nh)
@@ -393,20 +475,39 @@ namespace sb {
     __device__ __forceinline__ void convert_item(float* sm, const Params& prm, const Ctl& ctl, int buf, int rp, int lane)
     {
       using C = Cfg<TX>;
-      constexpr int BW = C::BOXW();
+      constexpr int BW = C::BOXW(), OFF0 = C::off_out(0), P0 = C::P(0), W0 = C::W(0);
       const float* raw = sm + buf * (2 * 8 * BW);
-      float* out = sm + C::off_out(0) + rp * C::P(0) * 2;
+      float* out = sm + OFF0 + rp * P0 * 2;
       const int xs = ctl.x0 - HALO;
-      for (int i = lane; i < C::P(0); i += 32)
+      for (int i = lane; i < P0; i += 32)
       {
-        int ic = min(i, C::W(0) - 1);
+        int ic = min(i, W0 - 1);
         const int xc = min(max(xs + ic, 0), prm.w - 1);
-        ic = min(max(xc - xs, 0), C::W(0) - 1);
+        ic = min(max(xc - xs, 0), W0 - 1);
         const int jc = ic + TMA_SKEW;  // column inside the two TMA boxes
         const int half = jc >= BW ? 1 : 0;
         const float* p = raw + half * (8 * BW) + (2 * rp) * BW + (jc - half * BW);
         *reinterpret_cast<float2*>(out + 2 * i) = make_float2(p[0], p[BW]);
       }
+    }
+
+    // Number of warp items of stage s's row / column pass at step t (0 when the stage's
+    // 8-row block lies outside the rows this CTA needs).
+    __device__ __forceinline__ int row_items(const Params& prm, const Ctl& ctl, int s, int t)
+    {
+      const StageDesc& sd = prm.sd[s];
+      const int u = t - (s - 1);
+      const int a = ctl.Y + 8 * u - sd.CSP;
+      const int lo = max(0, ctl.y0 - sd.HP), hi = min(prm.h, ctl.y1 + sd.HP);
+      return (u >= 0 && a + 7 >= lo && a < hi) ? sd.NWA : 0;
+    }
+    __device__ __forceinline__ int col_items(const Params& prm, const Ctl& ctl, int s, int t)
+    {
+      const StageDesc& sd = prm.sd[s];
+      const int u = t - (s - 1);
+      const int b = ctl.Y + 8 * u - sd.CSS;
+      const int lo = max(0, ctl.y0 - sd.HS), hi = min(prm.h, ctl.y1 + sd.HS);
+      return (u >= 0 && b + 7 >= lo && b < hi) ? sd.NWB : 0;
     }
 
     template <int TX>
@@ -416,8 +517,10 @@ namespace sb {
       using C = Cfg<TX>;
       extern __shared__ __align__(1024) unsigned char smem_raw[];
       float* sm = reinterpret_cast<float*>(smem_raw);
-      unsigned long long* bars = reinterpret_cast<unsigned long long*>(sm + C::total_floats());  // 2 mbarriers
-      int* ctr = reinterpret_cast<int*>(bars + 2);                                                // 4 phase counters
+      constexpr int TOTAL = C::total_floats(), OFF_TAB = C::off_rowtab();
+      int* rowtab = reinterpret_cast<int*>(sm + OFF_TAB);
+      unsigned long long* bars = reinterpret_cast<unsigned long long*>(sm + TOTAL);  // 2 mbarriers
+      int* ctr = reinterpret_cast<int*>(bars + 2);                                    // 4 phase counters
 
       const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
       Ctl ctl;
@@ -492,18 +595,25 @@ namespace sb {
 
         // ---------------- phase A: row passes of all stages ----------------
         {
+          // Ring-row table of this step's column passes (read after the barrier below):
+          // entry m of stage s = float offset of the ring row that holds image row
+          // clamp(b_s - c_s + m), b_s = first output row of stage s at this step.
+          if (tid < 5 * ROWTAB)
+          {
+            const int s = tid / ROWTAB + 1, m = tid - (s - 1) * ROWTAB;
+            const StageDesc& sd = prm.sd[s];
+            const int u = t - (s - 1);
+            const int b = ctl.Y + 8 * u - sd.CSS;
+            const int yc = min(max(b - sd.c + m, 0), h - 1);
+            const int origin = ctl.Y - sd.CSP - 8 * 48;  // row of ring slot 0, 48 blocks up (row_item: slot = (u + 48) % NB)
+            const int rr = yc - origin;                   // > 0
+            rowtab[tid] = (rr % sd.depth) * sd.PR;
+          }
           int cnt[6];
-          int total = 0;
 #pragma unroll
           for (int s = 5; s >= 1; --s)
-          {
-            const int u = t - (s - 1);
-            const int a = ctl.Y + 8 * u - CS_(s - 1);
-            const int lo = max(0, ctl.y0 - H_(s - 1)), hi = min(h, ctl.y1 + H_(s - 1));
-            const bool on = u >= 0 && a + 7 >= lo && a < hi;
-            cnt[s] = on ? C::NWA(s) : 0;
-            total += cnt[s];
-          }
+            cnt[s] = row_items(prm, ctl, s, t);
+          const int total = cnt[5] + cnt[4] + cnt[3] + cnt[2] + cnt[1];
           if (tid == 0)
             ctr[(phase + 2) & 3] = 0;
           int* my = &ctr[phase & 3];
@@ -515,16 +625,15 @@ namespace sb {
             id = __shfl_sync(0xffffffffu, id, 0);
             if (id >= total)
               break;
-            if (id < cnt[5])
-              row_item<TX, 5>(sm, prm, ctl, t, id, lane);
-            else if ((id -= cnt[5]) < cnt[4])
-              row_item<TX, 4>(sm, prm, ctl, t, id, lane);
-            else if ((id -= cnt[4]) < cnt[3])
-              row_item<TX, 3>(sm, prm, ctl, t, id, lane);
-            else if ((id -= cnt[3]) < cnt[2])
-              row_item<TX, 2>(sm, prm, ctl, t, id, lane);
-            else
-              row_item<TX, 1>(sm, prm, ctl, t, id - cnt[2], lane);
+            int s = 5;
+#pragma unroll
+            for (int e = 5; e >= 2; --e)
+              if (s == e && id >= cnt[e])
+              {
+                id -= cnt[e];
+                s = e - 1;
+              }
+            row_item(sm, prm, ctl, s, t, id, lane);
           }
           ++phase;
         }
@@ -533,17 +642,10 @@ namespace sb {
         // ---------------- phase B: column passes + staging of the next input block ----------------
         {
           int cnt[6];
-          int total = 0;
 #pragma unroll
           for (int s = 5; s >= 1; --s)
-          {
-            const int u = t - (s - 1);
-            const int b = ctl.Y + 8 * u - CS_(s);
-            const int lo = max(0, ctl.y0 - H_(s)), hi = min(h, ctl.y1 + H_(s));
-            const bool on = u >= 0 && b + 7 >= lo && b < hi;
-            cnt[s] = on ? C::NWB(s) : 0;
-            total += cnt[s];
-          }
+            cnt[s] = col_items(prm, ctl, s, t);
+          const int total = cnt[5] + cnt[4] + cnt[3] + cnt[2] + cnt[1];
           const bool stage_next = block_needed(t + 1);
           const int n_conv = stage_next ? 4 : 0;
           if (tid == 0)
@@ -557,21 +659,21 @@ namespace sb {
             id = __shfl_sync(0xffffffffu, id, 0);
             if (id >= total + n_conv)
               break;
-            if (id < cnt[5])
-              col_item<TX, 5>(sm, prm, ctl, t, id, lane);
-            else if ((id -= cnt[5]) < cnt[4])
-              col_item<TX, 4>(sm, prm, ctl, t, id, lane);
-            else if ((id -= cnt[4]) < cnt[3])
-              col_item<TX, 3>(sm, prm, ctl, t, id, lane);
-            else if ((id -= cnt[3]) < cnt[2])
-              col_item<TX, 2>(sm, prm, ctl, t, id, lane);
-            else if ((id -= cnt[2]) < cnt[1])
-              col_item<TX, 1>(sm, prm, ctl, t, id, lane);
-            else
+            if (id >= total)
             {
               wait_block(t + 1);
-              convert_item<TX>(sm, prm, ctl, (t + 1) & 1, id - cnt[1], lane);
+              convert_item<TX>(sm, prm, ctl, (t + 1) & 1, id - total, lane);
+              continue;
             }
+            int s = 5;
+#pragma unroll
+            for (int e = 5; e >= 2; --e)
+              if (s == e && id >= cnt[e])
+              {
+                id -= cnt[e];
+                s = e - 1;
+              }
+            col_item(sm, prm, ctl, s, t, id, lane);
           }
           ++phase;
         }
@@ -637,8 +739,29 @@ namespace sb {
       prm.npitch = next ? next->pitch : 0;
       prm.one = 1.f;
       for (int s = 1; s <= 5; ++s)
+      {
         for (int j = 0; j < K_(s); ++j)
-          prm.taps[s - 1][j] = taps[s].v[j];
+          prm.taps[s][j] = taps[s].v[j];
+        StageDesc& sd = prm.sd[s];
+        sd.K = K_(s);
+        sd.c = C_(s);
+        sd.depth = 8 * NB_(s);
+        sd.W = C::W(s);
+        sd.HS = H_(s);
+        sd.HP = H_(s - 1);
+        sd.CSP = CS_(s - 1);
+        sd.CSS = CS_(s);
+        sd.off_in = C::off_out(s - 1);
+        sd.P_in = C::P(s - 1);
+        sd.off_ring = C::off_ring(s);
+        sd.PR = C::PR(s);
+        sd.off_out = s < 5 ? C::off_out(s) : 0;
+        sd.P_out = s < 5 ? C::P(s) : 0;
+        sd.NCH4 = C::NCH4(s);
+        sd.NWA = C::NWA(s);
+        sd.NWB = C::NWB(s);
+      }
+      prm.sd[0].off_ring = C::off_rowtab();  // sd[0] carries the ring-row table offset
 
       const int n_strips = (oc.w + TX - 1) / TX;
       int n_segs = 148 / n_strips;
