@@ -142,6 +142,17 @@ SARA_B200_API void sara_b200_destroy(sara_b200_ctx* ctx);
 SARA_B200_API int sara_b200_host_alloc(void** ptr, uint64_t bytes);
 SARA_B200_API void sara_b200_host_free(void* ptr);
 
+/* Which kernels build the Gaussian / DoG pyramid.  All modes produce the same bits; the
+ * choice exists for benchmarking and parity tests.  AUTO picks the fastest measured one. */
+typedef enum sara_b200_pyramid_mode
+{
+  SARA_B200_PYRAMID_AUTO = 0,
+  SARA_B200_PYRAMID_GENERIC = 1, /* one launch per scale, any tap count */
+  SARA_B200_PYRAMID_STAGE = 2,   /* TMA-staged marching kernel, one launch per scale (default schedule) */
+  SARA_B200_PYRAMID_FUSED = 3    /* TMA-staged fused octave kernel, one launch per octave (default schedule) */
+} sara_b200_pyramid_mode;
+SARA_B200_API int sara_b200_set_pyramid_mode(sara_b200_ctx* ctx, int mode);
+
 /* Record CUDA events around the stages (sara_b200_last_timings). */
 SARA_B200_API int sara_b200_set_profiling(sara_b200_ctx* ctx, int on);
 SARA_B200_API int sara_b200_last_timings(sara_b200_ctx* ctx, int slot, sara_b200_timings* out);

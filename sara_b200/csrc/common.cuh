@@ -82,6 +82,13 @@ namespace sb {
   int launch_fused_octave(const OctaveDesc& oct, const OctaveDesc* next, int downscale_index,
                           const Taps* taps, int n_scales, cudaStream_t st);
 
+  // Single-stage marching kernel (pyramid_stage.cu): G(s-1) -> G(s), D(s-1), optionally the
+  // base of the next octave; for the tap counts of the default schedule.
+  bool stage_kernel_supported(int n_taps);
+  bool launch_stage(const float* src, int src_pitch, float* dst, float* dog, float* nextG, int w, int h,
+                    int pitch, int nw, int nh, int npitch, const Taps& taps, cudaStream_t st);
+  bool downscale_is_even_sampling(int sw, int sh, int dw, int dh);
+
   struct ExtremaParams
   {
     float extremum_thres;

@@ -69,6 +69,7 @@ struct sara_b200_ctx
   sara_b200_limits lim{};
   int cap_kp = 0, cap_ext = 0, cap_cand = 0;
   bool profiling = false;
+  int pyramid_mode = SARA_B200_PYRAMID_AUTO;
   std::vector<Slot> slots;
   char err[512] = "";
 };
@@ -367,16 +368,57 @@ namespace {
           launch_downscale(full, w, h, w, o0.G, o0.w, o0.h, o0.pitch, st);
         }
         else if (g.pre_sigma > 0.f)
-          launch_gaussian_stage(d_src, w, o0.G, o0.pitch, nullptr, 0, w, h, pre, st);
+        {
+          // fo == 0: base = gaussian(image, sqrt(s0^2 - s_cam^2)), GaussianPyramid.hpp:69-73
+          const bool fast = ctx->pyramid_mode != SARA_B200_PYRAMID_GENERIC && stage_kernel_supported(pre.n) &&
+                            launch_stage(d_src, w, o0.G, nullptr, nullptr, w, h, o0.pitch, 0, 0, 0, pre, st);
+          if (!fast)
+            launch_gaussian_stage(d_src, w, o0.G, o0.pitch, nullptr, 0, w, h, pre, st);
+        }
         else
           launch_copy2d(d_src, w, o0.G, o0.pitch, w, h, st);
         ++S.pyramid_launches;
       }
-      const bool fused = fused_octave_supported(S.stage_taps.data(), P.n_scales);
+      // Which kernels build an octave (sara_b200_set_pyramid_mode): the per-stage marching
+      // kernel and the fused octave kernel cover the tap counts of the default schedule; any
+      // other schedule runs on the generic kernel.
+      const int mode = ctx->pyramid_mode;
+      const bool fused = mode == SARA_B200_PYRAMID_FUSED && fused_octave_supported(S.stage_taps.data(), P.n_scales);
+      bool staged = (mode == SARA_B200_PYRAMID_AUTO || mode == SARA_B200_PYRAMID_STAGE) && P.n_scales > 1;
+      for (int s = 1; s < P.n_scales && staged; ++s)
+        staged = stage_kernel_supported(S.stage_taps[s].n);
       for (int o = 0; o < P.n_octaves; ++o)
       {
         const OctaveDesc& oc = P.oct[o];
         const OctaveDesc* next = o + 1 < P.n_octaves ? &P.oct[o + 1] : nullptr;
+        if (staged)
+        {
+          const bool fuse_down = next != nullptr && S.downscale_index >= 1 &&
+                                 downscale_is_even_sampling(oc.w, oc.h, next->w, next->h);
+          for (int s = 1; s < P.n_scales; ++s)
+          {
+            const bool down = fuse_down && s == S.downscale_index;
+            if (!launch_stage(oc.G + static_cast<size_t>(s - 1) * oc.layer_stride, oc.pitch,
+                              oc.G + static_cast<size_t>(s) * oc.layer_stride,
+                              oc.D + static_cast<size_t>(s - 1) * oc.layer_stride, down ? next->G : nullptr, oc.w, oc.h,
+                              oc.pitch, down ? next->w : 0, down ? next->h : 0, down ? next->pitch : 0, S.stage_taps[s],
+                              st))
+              return fail(ctx, SARA_B200_ERR_CUDA, "stage kernel could not be launched (tensor map / attributes)");
+            ++S.pyramid_launches;
+            if (next && !fuse_down && s == S.downscale_index)
+            {
+              launch_downscale(oc.G + static_cast<size_t>(s) * oc.layer_stride, oc.w, oc.h, oc.pitch, next->G, next->w,
+                               next->h, next->pitch, st);
+              ++S.pyramid_launches;
+            }
+          }
+          if (next && !fuse_down && S.downscale_index == 0)
+          {
+            launch_downscale(oc.G, oc.w, oc.h, oc.pitch, next->G, next->w, next->h, next->pitch, st);
+            ++S.pyramid_launches;
+          }
+          continue;
+        }
         if (fused)
         {
           const int n = launch_fused_octave(oc, next, S.downscale_index, S.stage_taps.data(), P.n_scales, st);
@@ -689,6 +731,16 @@ int sara_b200_set_profiling(sara_b200_ctx* ctx, int on)
   if (!ctx)
     return SARA_B200_ERR_BAD_ARG;
   ctx->profiling = on != 0;
+  return 0;
+}
+
+int sara_b200_set_pyramid_mode(sara_b200_ctx* ctx, int mode)
+{
+  if (!ctx)
+    return SARA_B200_ERR_BAD_ARG;
+  if (mode < SARA_B200_PYRAMID_AUTO || mode > SARA_B200_PYRAMID_FUSED)
+    return fail(ctx, SARA_B200_ERR_BAD_ARG, "unknown pyramid mode %d", mode);
+  ctx->pyramid_mode = mode;
   return 0;
 }
 

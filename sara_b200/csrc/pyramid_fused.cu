@@ -34,12 +34,11 @@
 #include <cstdio>
 
 #include "common.cuh"
+#include "fp32x2_tma.cuh"
 
 namespace sb {
 
   namespace fused {
-
-    typedef unsigned long long u64;
 
     constexpr int NT = 640;  // threads per CTA (20 warps)
     constexpr int HALO = 41;  // 5 + 6 + 8 + 10 + 12
@@ -131,66 +130,6 @@ namespace sb {
     {
       int x0, y0, y1, Y;
     };
-
-    // ---- packed fp32x2 arithmetic -----------------------------------------------
-    __device__ __forceinline__ u64 pack2(float lo, float hi)
-    {
-      u64 r;
-      asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-      return r;
-    }
-    __device__ __forceinline__ float lo2(u64 v) { return __uint_as_float(static_cast<unsigned>(v)); }
-    __device__ __forceinline__ float hi2(u64 v) { return __uint_as_float(static_cast<unsigned>(v >> 32)); }
-    __device__ __forceinline__ u64 mul2(u64 a, u64 b)
-    {
-      u64 r;
-      asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-      return r;
-    }
-    // RN(acc + p) as acc * ONE + p (see the header comment).
-    __device__ __forceinline__ u64 add2(u64 acc, u64 p, u64 one)
-    {
-      u64 r;
-      asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(acc), "l"(one), "l"(p));
-      return r;
-    }
-
-    // ---- TMA / mbarrier ------------------------------------------------------------
-    __device__ __forceinline__ unsigned smem_u32(const void* p)
-    {
-      return static_cast<unsigned>(__cvta_generic_to_shared(p));
-    }
-    __device__ __forceinline__ void mbar_init(void* bar, int count)
-    {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-    }
-    __device__ __forceinline__ void mbar_expect_tx(void* bar, unsigned bytes)
-    {
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                   : "memory");
-    }
-    __device__ __forceinline__ void mbar_wait(void* bar, unsigned parity)
-    {
-      asm volatile(
-          "{\n"
-          ".reg .pred p;\n"
-          "WAIT_%=:\n"
-          "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-          "@p bra DONE_%=;\n"
-          "bra WAIT_%=;\n"
-          "DONE_%=:\n"
-          "}\n" ::"r"(smem_u32(bar)),
-          "r"(parity)
-          : "memory");
-    }
-    __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, void* bar)
-    {
-      asm volatile(
-          "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-          ::"r"(smem_u32(dst)),
-          "l"(reinterpret_cast<unsigned long long>(map)), "r"(x), "r"(y), "r"(smem_u32(bar))
-          : "memory");
-    }
 
     // One block of NTAP consecutive taps on a register window: acc[q] += w[q + jj] * k[jb + jj].
     template <int NTAP>
@@ -682,10 +621,6 @@ namespace sb {
     }
 
     // ---- host side ------------------------------------------------------------------------
-    typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
     EncodeTiledFn encode_fn()
     {
       static EncodeTiledFn fn = [] {
@@ -794,7 +729,7 @@ namespace sb {
   // downscale(): dst(x, y) = src(int(x * sx), int(y * sy)) with float ratios
   // (Resize.cpp:31-61).  The fused kernel emits src(2x, 2y); this checks that the
   // two agree for the sizes at hand (they do for every size met so far).
-  static bool downscale_is_even_sampling(int sw, int sh, int dw, int dh)
+  bool downscale_is_even_sampling(int sw, int sh, int dw, int dh)
   {
     const float sx = static_cast<float>(sw) / static_cast<float>(dw);
     const float sy = static_cast<float>(sh) / static_cast<float>(dh);

@@ -5,8 +5,10 @@ from sara_b200 import synthetic as S
 from oracle import oracle as O
 from parity import assert_pyramids_identical
 w, h = int(sys.argv[1]), int(sys.argv[2])
+mode = sys.argv[3] if len(sys.argv) > 3 else 'auto'
 img = S.tex(w, h, 7)
 ctx = sb.SiftContext(max(w, 64), max(h, 64))
+ctx.set_pyramid_mode(mode)
 ctx.pyramid_enqueue(0, img, sb.ImagePyramidParams(first_octave_index=0))
 ctx.wait(0)
 ref = O.compute_dog_extrema(img, O.PyramidParams(first_octave_index=0))
