@@ -60,6 +60,9 @@ namespace sb {
     int n_ext;
     int n_kp;
     int overflow;  // bit 0: candidates, bit 1: extrema, bit 2: keypoints
+    int ori_next;  // work queues of the orientation / descriptor kernels (next keypoint to take)
+    int desc_next;
+    int pad[2];
   };
 
   typedef sara_b200_keypoint Keypoint;

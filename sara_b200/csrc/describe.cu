@@ -194,19 +194,59 @@ namespace sb {
 
     constexpr int DESC_WARPS = 4;
 
+    // atan2 for the descriptor's soft orientation binning: odd minimax polynomial on [0, 1]
+    // (|error| < 1e-5 rad, i.e. 1.3e-5 of a bin; the binning is continuous in the angle, so this
+    // stays far inside the descriptor tolerance).  The dominant-orientation kernel keeps atan2f:
+    // its binning is a hard floor().
+    __device__ __forceinline__ float fast_atan2(float y, float x)
+    {
+      const float ax = fabsf(x), ay = fabsf(y);
+      const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+      const float a = mx > 0.f ? __fdividef(mn, mx) : 0.f;
+      const float s = __fmul_rn(a, a);
+      float r = __fmaf_rn(s, -0.0117212f, 0.05265332f);
+      r = __fmaf_rn(r, s, -0.11643287f);
+      r = __fmaf_rn(r, s, 0.19354346f);
+      r = __fmaf_rn(r, s, -0.33262347f);
+      r = __fmaf_rn(r, s, 0.99997726f);
+      r = __fmul_rn(r, a);
+      r = ay > ax ? __fsub_rn(1.57079637f, r) : r;
+      r = x < 0.f ? __fsub_rn(kPi, r) : r;
+      return y < 0.f ? -r : r;
+    }
+
+    __device__ __forceinline__ float approx_sqrt(float v)
+    {
+      float r;
+      asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+      return r;
+    }
+
+    // One warp per keypoint, keypoints handed out through a device-side queue (their cost
+    // varies with the square of the scale).  The window of ComputeSIFTDescriptor (SIFT.hpp:62-145)
+    // is the bounding square of the ROTATED 4x4 grid, so about half of its pixels fall outside
+    // the grid: a cheap geometric test runs on all pixels, the survivors are compacted through a
+    // small per-warp queue (ballot + popc), and the expensive part (gradient, atan2, exp,
+    // trilinear update of 8 bins) runs on full warps.
     __global__ void __launch_bounds__(DESC_WARPS * 32)
         descriptor_kernel(const __grid_constant__ PyramidDesc P, const Keypoint* __restrict__ kp_oct,
-                          const Counters* __restrict__ counters, int cap_kp,
-                          Keypoint* __restrict__ kp_out, float* __restrict__ desc)
+                          Counters* __restrict__ counters, int cap_kp, Keypoint* __restrict__ kp_out,
+                          float* __restrict__ desc)
     {
-      extern __shared__ float s_dyn[];  // DESC_WARPS x 128 x 32 lane-private bins
+      extern __shared__ float s_dyn[];  // DESC_WARPS x (128 x 32 lane-private bins + 64 queue entries)
       const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-      float* priv = s_dyn + wid * (128 * 32);
+      float* priv = s_dyn + wid * (128 * 32 + 64);
+      int* queue = reinterpret_cast<int*>(priv + 128 * 32);
       const int n = min(counters->n_kp, cap_kp);
-      const int warps_per_grid = gridDim.x * DESC_WARPS;
 
-      for (int i = blockIdx.x * DESC_WARPS + wid; i < n; i += warps_per_grid)
+      while (true)
       {
+        int i = 0;
+        if (lane == 0)
+          i = atomicAdd(&counters->desc_next, 1);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= n)
+          break;
         const Keypoint kp = kp_oct[i];
         const OctaveDesc& oc = P.oct[kp.o];
         const float* G = oc.G + static_cast<size_t>(kp.s) * oc.layer_stride;
@@ -227,64 +267,99 @@ namespace sb {
         const int rx = static_cast<int>(roundf(kp.x));
         const int ry = static_cast<int>(roundf(kp.y));
 
+#pragma unroll 8
         for (int b = 0; b < 128; ++b)
           priv[b * 32 + lane] = 0.f;
 
-        const int side = 2 * rounded_r + 1;
-        const int count = side * side;
-        for (int t = lane; t < count; t += 32)
-        {
-          const int v = t / side - rounded_r;
-          const int u = t - (v + rounded_r) * side - rounded_r;
+        // trilinear accumulate() of one kept sample (SIFT.hpp:204-238) into the lane's bins
+        auto heavy = [&](int uv) {
+          const int u = static_cast<short>(uv & 0xffff), v = uv >> 16;
           const int X = rx + u, Y = ry + v;
-          if (X < 0 || X >= w || Y < 0 || Y >= h)
-            continue;
           const float fu = static_cast<float>(u), fv = static_cast<float>(v);
           float px = __fadd_rn(__fmul_rn(T00, fu), __fmul_rn(T01, fv));
           float py = __fadd_rn(__fmul_rn(T10, fu), __fmul_rn(T11, fv));
-          const float wexp = __fdiv_rn(-__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), 8.f);
+          const float weight = __expf(__fmul_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), -0.125f));
           px = __fadd_rn(px, 1.5f);
           py = __fadd_rn(py, 1.5f);
-          if (fminf(px, py) <= -1.f || fmaxf(px, py) >= 4.f)
-            continue;
-          const float weight = expf(wexp);
-          float mag, ori;
-          polar_gradient(G, w, h, pitch, X, Y, mag, ori);
-          ori = __fsub_rn(ori, theta);
-          ori = ori < 0.f ? __fadd_rn(ori, __fmul_rn(2.f, kPi)) : ori;
-          ori = __fmul_rn(ori, __fdiv_rn(8.f, __fmul_rn(2.f, kPi)));
-
-          // accumulate(), SIFT.hpp:204-238: std::modf truncates toward zero (quirk N6).
+          // gradient_polar_coordinates on the fly: (2 |g|, atan2), one-sided at the borders
+          const float* row = G + static_cast<size_t>(Y) * pitch;
+          const int xn = X == w - 1 ? X : X + 1, xp = X == 0 ? X : X - 1;
+          const int yn = Y == h - 1 ? Y : Y + 1, yp = Y == 0 ? Y : Y - 1;
+          const float dx = __fsub_rn(__ldg(row + xn), __ldg(row + xp));
+          const float dy = __fsub_rn(__ldg(G + static_cast<size_t>(yn) * pitch + X),
+                                     __ldg(G + static_cast<size_t>(yp) * pitch + X));
+          const float mag = approx_sqrt(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));  // = 2 |(dx, dy) / 2|
+          float ori = __fsub_rn(fast_atan2(dy, dx), theta);
+          ori = ori < 0.f ? __fadd_rn(ori, kTwoPi) : ori;
+          ori = __fmul_rn(ori, 1.27323954f);  // 8 / (2 pi)
+          // std::modf truncates toward zero (quirk N6)
           const float xif = truncf(px), yif = truncf(py), oif = truncf(ori);
           const float xfrac = __fsub_rn(px, xif), yfrac = __fsub_rn(py, yif), ofrac = __fsub_rn(ori, oif);
           const int xi = static_cast<int>(xif), yi = static_cast<int>(yif), oi = static_cast<int>(oif);
+          const float wm = __fmul_rn(weight, mag);
+          const float wo1 = __fmul_rn(ofrac, wm), wo0 = __fsub_rn(wm, wo1);
+          const int o0 = oi & 7, o1 = (oi + 1) & 7;
 #pragma unroll
-          for (int dy = 0; dy < 2; ++dy)
+          for (int dyy = 0; dyy < 2; ++dyy)
           {
-            const int yy = yi + dy;
+            const int yy = yi + dyy;
             if (yy < 0 || yy >= 4)
               continue;
-            const float wy = dy == 0 ? __fsub_rn(1.f, yfrac) : yfrac;
+            const float wy = dyy == 0 ? __fsub_rn(1.f, yfrac) : yfrac;
 #pragma unroll
-            for (int dx = 0; dx < 2; ++dx)
+            for (int dxx = 0; dxx < 2; ++dxx)
             {
-              const int xx = xi + dx;
+              const int xx = xi + dxx;
               if (xx < 0 || xx >= 4)
                 continue;
-              const float wx = dx == 0 ? __fsub_rn(1.f, xfrac) : xfrac;
-#pragma unroll
-              for (int dori = 0; dori < 2; ++dori)
-              {
-                const int oo = (oi + dori) % 8;
-                const float wo = dori == 0 ? __fsub_rn(1.f, ofrac) : ofrac;
-                const float contrib =
-                    __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(wy, wx), wo), weight), mag);
-                float* bin = priv + (32 * yy + xx * 8 + oo) * 32 + lane;
-                *bin = __fadd_rn(*bin, contrib);
-              }
+              const float wxy = __fmul_rn(wy, dxx == 0 ? __fsub_rn(1.f, xfrac) : xfrac);
+              float* cell = priv + (32 * yy + 8 * xx) * 32 + lane;
+              cell[o0 * 32] = __fadd_rn(cell[o0 * 32], __fmul_rn(wxy, wo0));
+              cell[o1 * 32] = __fadd_rn(cell[o1 * 32], __fmul_rn(wxy, wo1));
             }
           }
+        };
+
+        const int side = 2 * rounded_r + 1;
+        const int count = side * side;
+        int q_n = 0;  // entries waiting in the queue (< 32 between rounds)
+        for (int t0 = 0; t0 < count; t0 += 32)
+        {
+          const int t = t0 + lane;
+          bool keep = false;
+          int uv = 0;
+          if (t < count)
+          {
+            const int vv = t / side;
+            const int v = vv - rounded_r;
+            const int u = t - vv * side - rounded_r;
+            const int X = rx + u, Y = ry + v;
+            const float fu = static_cast<float>(u), fv = static_cast<float>(v);
+            const float px = __fadd_rn(__fadd_rn(__fmul_rn(T00, fu), __fmul_rn(T01, fv)), 1.5f);
+            const float py = __fadd_rn(__fadd_rn(__fmul_rn(T10, fu), __fmul_rn(T11, fv)), 1.5f);
+            keep = X >= 0 && X < w && Y >= 0 && Y < h && fminf(px, py) > -1.f && fmaxf(px, py) < 4.f;
+            uv = (u & 0xffff) | (v << 16);
+          }
+          const unsigned m = __ballot_sync(0xffffffffu, keep);
+          if (keep)
+            queue[(q_n + __popc(m & ((1u << lane) - 1u))) & 63] = uv;
+          q_n += __popc(m);
+          __syncwarp();
+          if (q_n >= 32)
+          {
+            heavy(queue[lane]);
+            // move the leftover (< 32 entries) to the front
+            const int rest = q_n - 32;
+            const int moved = lane < rest ? queue[32 + lane] : 0;
+            __syncwarp();
+            if (lane < rest)
+              queue[lane] = moved;
+            q_n = rest;
+            __syncwarp();
+          }
         }
+        if (lane < q_n)
+          heavy(queue[lane]);
         __syncwarp();
 
         // Fixed-order reduction: lane owns bins lane, lane+32, lane+64, lane+96.
@@ -360,7 +435,7 @@ namespace sb {
   int launch_descriptors(const PyramidDesc& P, const Keypoint* kp_oct, Keypoint* kp_out, float* desc,
                          int cap_kp, Counters* counters, cudaStream_t st)
   {
-    const int smem = DESC_WARPS * 128 * 32 * sizeof(float);
+    const int smem = DESC_WARPS * (128 * 32 + 64) * sizeof(float);
     cudaFuncSetAttribute(descriptor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     descriptor_kernel<<<148 * 3, DESC_WARPS * 32, smem, st>>>(P, kp_oct, counters, cap_kp, kp_out, desc);
     return 1;

@@ -114,18 +114,47 @@ namespace sb {
           continue;
         int out = seg_off[seg] + seg_chunk_off[seg >> 10];
         const uint8_t* row = oc.map + (static_cast<size_t>(s - 1) * oc.h + y) * oc.w;
-        for (int x0 = 0; x0 < oc.w; x0 += 32)
+        // The map is almost empty: scan it 4 bytes per lane (128 pixels per warp step) and
+        // only expand the words that hold a candidate.  Order inside a row = x order.
+        const int w = oc.w;
+        const int mis = static_cast<int>(reinterpret_cast<uintptr_t>(row) & 3u);  // row start inside its 4-byte word
+        const uint32_t* words = reinterpret_cast<const uint32_t*>(row - mis);
+        const int n_words = (mis + w + 3) >> 2;
+        for (int w0 = 0; w0 < n_words; w0 += 32)
         {
-          const int x = x0 + lane;
-          const uint8_t t = x < oc.w ? row[x] : 0;
-          const unsigned m = __ballot_sync(0xffffffffu, t != 0);
-          if (t != 0)
+          const int wi = w0 + lane;
+          uint32_t v = wi < n_words ? __ldg(words + wi) : 0u;
+          // mask bytes outside [row, row + w)
+          const int x_first = 4 * wi - mis;
+#pragma unroll
+          for (int b = 0; b < 4; ++b)
+            if (x_first + b < 0 || x_first + b >= w)
+              v &= ~(0xffu << (8 * b));
+          const int mine = (v & 0xffu ? 1 : 0) + (v & 0xff00u ? 1 : 0) + (v & 0xff0000u ? 1 : 0) + (v >> 24 ? 1 : 0);
+          if (__ballot_sync(0xffffffffu, mine != 0) == 0u)
+            continue;
+          // exclusive prefix of `mine` across the warp
+          int inc = mine;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1)
           {
-            const int pos = out + __popc(m & ((1u << lane) - 1u));
-            if (pos < cap_cand)
-              cand[pos] = Candidate{x, y, (o << 8) | s, t};
+            const int t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d)
+              inc += t;
           }
-          out += __popc(m);
+          int pos = out + inc - mine;
+#pragma unroll
+          for (int b = 0; b < 4; ++b)
+          {
+            const uint32_t t = (v >> (8 * b)) & 0xffu;
+            if (t != 0)
+            {
+              if (pos < cap_cand)
+                cand[pos] = Candidate{x_first + b, y, (o << 8) | s, static_cast<int>(t)};
+              ++pos;
+            }
+          }
+          out += __shfl_sync(0xffffffffu, inc, 31);
         }
       }
     }
