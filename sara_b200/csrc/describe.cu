@@ -233,9 +233,9 @@ namespace sb {
                           Counters* __restrict__ counters, int cap_kp, Keypoint* __restrict__ kp_out,
                           float* __restrict__ desc)
     {
-      extern __shared__ float s_dyn[];  // DESC_WARPS x (128 x 32 lane-private bins + 64 queue entries)
+      extern __shared__ float s_dyn[];  // DESC_WARPS x (128 x 32 lane-private bins + 128 queue entries)
       const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-      float* priv = s_dyn + wid * (128 * 32 + 64);
+      float* priv = s_dyn + wid * (128 * 32 + 128);
       int* queue = reinterpret_cast<int*>(priv + 128 * 32);
       const int n = min(counters->n_kp, cap_kp);
 
@@ -271,23 +271,42 @@ namespace sb {
         for (int b = 0; b < 128; ++b)
           priv[b * 32 + lane] = 0.f;
 
-        // trilinear accumulate() of one kept sample (SIFT.hpp:204-238) into the lane's bins
-        auto heavy = [&](int uv) {
+        // A kept sample in two steps, so that the loads of several samples are in flight
+        // together: fetch() issues the four gradient loads, finish() does the trilinear
+        // accumulate() (SIFT.hpp:204-238) into the lane's private bins.
+        struct Sample
+        {
+          float fu, fv, xn, xp, yn, yp;
+        };
+        auto fetch = [&](int uv, bool on) {
+          Sample sm;
           const int u = static_cast<short>(uv & 0xffff), v = uv >> 16;
-          const int X = rx + u, Y = ry + v;
-          const float fu = static_cast<float>(u), fv = static_cast<float>(v);
-          float px = __fadd_rn(__fmul_rn(T00, fu), __fmul_rn(T01, fv));
-          float py = __fadd_rn(__fmul_rn(T10, fu), __fmul_rn(T11, fv));
+          sm.fu = static_cast<float>(u);
+          sm.fv = static_cast<float>(v);
+          sm.xn = sm.xp = sm.yn = sm.yp = 0.f;
+          if (on)
+          {
+            // gradient_polar_coordinates on the fly, one-sided differences at the borders
+            const int X = rx + u, Y = ry + v;
+            const float* row = G + static_cast<size_t>(Y) * pitch;
+            const int xn = X == w - 1 ? X : X + 1, xp = X == 0 ? X : X - 1;
+            const int yn = Y == h - 1 ? Y : Y + 1, yp = Y == 0 ? Y : Y - 1;
+            sm.xn = __ldg(row + xn);
+            sm.xp = __ldg(row + xp);
+            sm.yn = __ldg(G + static_cast<size_t>(yn) * pitch + X);
+            sm.yp = __ldg(G + static_cast<size_t>(yp) * pitch + X);
+          }
+          return sm;
+        };
+        auto finish = [&](const Sample& sm, bool on) {
+          if (!on)
+            return;
+          float px = __fadd_rn(__fmul_rn(T00, sm.fu), __fmul_rn(T01, sm.fv));
+          float py = __fadd_rn(__fmul_rn(T10, sm.fu), __fmul_rn(T11, sm.fv));
           const float weight = __expf(__fmul_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), -0.125f));
           px = __fadd_rn(px, 1.5f);
           py = __fadd_rn(py, 1.5f);
-          // gradient_polar_coordinates on the fly: (2 |g|, atan2), one-sided at the borders
-          const float* row = G + static_cast<size_t>(Y) * pitch;
-          const int xn = X == w - 1 ? X : X + 1, xp = X == 0 ? X : X - 1;
-          const int yn = Y == h - 1 ? Y : Y + 1, yp = Y == 0 ? Y : Y - 1;
-          const float dx = __fsub_rn(__ldg(row + xn), __ldg(row + xp));
-          const float dy = __fsub_rn(__ldg(G + static_cast<size_t>(yn) * pitch + X),
-                                     __ldg(G + static_cast<size_t>(yp) * pitch + X));
+          const float dx = __fsub_rn(sm.xn, sm.xp), dy = __fsub_rn(sm.yn, sm.yp);
           const float mag = approx_sqrt(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));  // = 2 |(dx, dy) / 2|
           float ori = __fsub_rn(fast_atan2(dy, dx), theta);
           ori = ori < 0.f ? __fadd_rn(ori, kTwoPi) : ori;
@@ -319,10 +338,20 @@ namespace sb {
             }
           }
         };
+        // Processes queue entries [0, m), m <= 96, three per lane with their loads overlapped.
+        auto drain = [&](int m) {
+          const bool on0 = lane < m, on1 = lane + 32 < m, on2 = lane + 64 < m;
+          const Sample a = fetch(queue[lane], on0);
+          const Sample b = fetch(queue[lane + 32], on1);
+          const Sample c = fetch(queue[lane + 64], on2);
+          finish(a, on0);
+          finish(b, on1);
+          finish(c, on2);
+        };
 
         const int side = 2 * rounded_r + 1;
         const int count = side * side;
-        int q_n = 0;  // entries waiting in the queue (< 32 between rounds)
+        int q_n = 0;  // entries waiting in the queue (< 96 between rounds)
         for (int t0 = 0; t0 < count; t0 += 32)
         {
           const int t = t0 + lane;
@@ -342,15 +371,15 @@ namespace sb {
           }
           const unsigned m = __ballot_sync(0xffffffffu, keep);
           if (keep)
-            queue[(q_n + __popc(m & ((1u << lane) - 1u))) & 63] = uv;
+            queue[q_n + __popc(m & ((1u << lane) - 1u))] = uv;
           q_n += __popc(m);
           __syncwarp();
-          if (q_n >= 32)
+          if (q_n >= 96)
           {
-            heavy(queue[lane]);
+            drain(96);
             // move the leftover (< 32 entries) to the front
-            const int rest = q_n - 32;
-            const int moved = lane < rest ? queue[32 + lane] : 0;
+            const int rest = q_n - 96;
+            const int moved = lane < rest ? queue[96 + lane] : 0;
             __syncwarp();
             if (lane < rest)
               queue[lane] = moved;
@@ -358,8 +387,7 @@ namespace sb {
             __syncwarp();
           }
         }
-        if (lane < q_n)
-          heavy(queue[lane]);
+        drain(q_n);
         __syncwarp();
 
         // Fixed-order reduction: lane owns bins lane, lane+32, lane+64, lane+96.
@@ -435,7 +463,7 @@ namespace sb {
   int launch_descriptors(const PyramidDesc& P, const Keypoint* kp_oct, Keypoint* kp_out, float* desc,
                          int cap_kp, Counters* counters, cudaStream_t st)
   {
-    const int smem = DESC_WARPS * (128 * 32 + 64) * sizeof(float);
+    const int smem = DESC_WARPS * (128 * 32 + 128) * sizeof(float);
     cudaFuncSetAttribute(descriptor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     descriptor_kernel<<<148 * 3, DESC_WARPS * 32, smem, st>>>(P, kp_oct, counters, cap_kp, kp_out, desc);
     return 1;

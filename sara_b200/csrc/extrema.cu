@@ -44,25 +44,35 @@ namespace sb {
         // test goes first.
         if (!(fabsf(v) < __fmul_rn(0.8f, ep.extremum_thres)))
         {
-          const float* Dp = Dc - oct.layer_stride;
-          const float* Dn = Dc + oct.layer_stride;
+          // LocalScaleSpaceExtremum (Extrema.hpp:63-75): v >= (<=) all 26 neighbours.  The 8
+          // neighbours of the same layer decide for most pixels, so they go first and the
+          // two adjacent layers are only touched by pixels that are still candidates.
           bool is_max = true, is_min = true;
 #pragma unroll
           for (int dy = -1; dy <= 1; ++dy)
 #pragma unroll
             for (int dx = -1; dx <= 1; ++dx)
-            {
-              const float a = ld(Dp, pitch, x + dx, y + dy);
-              const float b = ld(Dn, pitch, x + dx, y + dy);
-              is_max = is_max && (v >= a) && (v >= b);
-              is_min = is_min && (v <= a) && (v <= b);
               if (dx != 0 || dy != 0)
               {
                 const float cc = ld(Dc, pitch, x + dx, y + dy);
                 is_max = is_max && (v >= cc);
                 is_min = is_min && (v <= cc);
               }
-            }
+          if (is_max || is_min)
+          {
+            const float* Dp = Dc - oct.layer_stride;
+            const float* Dn = Dc + oct.layer_stride;
+#pragma unroll
+            for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+              for (int dx = -1; dx <= 1; ++dx)
+              {
+                const float a = ld(Dp, pitch, x + dx, y + dy);
+                const float b = ld(Dn, pitch, x + dx, y + dy);
+                is_max = is_max && (v >= a) && (v >= b);
+                is_min = is_min && (v <= a) && (v <= b);
+              }
+          }
           if (is_max || is_min)
           {
             // on_edge(): Hessian functor, ImageProcessing/Differential.hpp:191-226.
