@@ -125,6 +125,8 @@ typedef struct sara_b200_timings
   float total;       /* first kernel to last kernel */
   int32_t pyramid_launches; /* kernels launched by the pyramid stage */
   int32_t total_launches;   /* kernels launched for the frame */
+  float pyramid_top_kernel;        /* the pyramid's longest launch (most taps, octave 0), ms; 0 if not measured */
+  float pyramid_top_kernel_mbytes; /* its algorithmic HBM traffic in MB */
 } sara_b200_timings;
 
 SARA_B200_API int sara_b200_version(void);

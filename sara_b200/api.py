@@ -71,6 +71,7 @@ class Timings(C.Structure):
         ("upload", C.c_float), ("pyramid", C.c_float), ("extrema", C.c_float),
         ("orientation", C.c_float), ("descriptor", C.c_float), ("total", C.c_float),
         ("pyramid_launches", C.c_int32), ("total_launches", C.c_int32),
+        ("pyramid_top_kernel", C.c_float), ("pyramid_top_kernel_mbytes", C.c_float),
     ]
 
     def asdict(self):

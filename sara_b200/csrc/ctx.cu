@@ -56,7 +56,8 @@ namespace {
     std::vector<Taps> stage_taps;  // per scale s >= 1
     bool busy = false;
     bool has_keypoints = false;  // the last frame ran the keypoint stages
-    cudaEvent_t ev[7] = {};
+    cudaEvent_t ev[9] = {};  // [7], [8]: around the pyramid's longest launch
+    double top_kernel_bytes = 0.;
     sara_b200_timings timings{};
     int pyramid_launches = 0, total_launches = 0;
   };
@@ -326,6 +327,7 @@ namespace {
       return rc;
     S.stream = st;
     S.pyramid_launches = 0;
+    S.top_kernel_bytes = 0.;
     const bool prof = ctx->profiling;
     if (prof)
       CU(ctx, cudaEventRecord(S.ev[0], st));
@@ -398,6 +400,13 @@ namespace {
           for (int s = 1; s < P.n_scales; ++s)
           {
             const bool down = fuse_down && s == S.downscale_index;
+            // The launch with the most taps on the largest octave is the pyramid's longest kernel.
+            const bool top = prof && o == 0 && s == P.n_scales - 1;
+            if (top)
+            {
+              CU(ctx, cudaEventRecord(S.ev[7], st));
+              S.top_kernel_bytes = 12.0 * oc.w * oc.h;  // reads G(s-1), writes G(s) and D(s-1): 3 x 4 B per pixel
+            }
             if (!launch_stage(oc.G + static_cast<size_t>(s - 1) * oc.layer_stride, oc.pitch,
                               oc.G + static_cast<size_t>(s) * oc.layer_stride,
                               oc.D + static_cast<size_t>(s - 1) * oc.layer_stride, down ? next->G : nullptr, oc.w, oc.h,
@@ -405,6 +414,8 @@ namespace {
                               st))
               return fail(ctx, SARA_B200_ERR_CUDA, "stage kernel could not be launched (tensor map / attributes)");
             ++S.pyramid_launches;
+            if (top)
+              CU(ctx, cudaEventRecord(S.ev[8], st));
             if (next && !fuse_down && s == S.downscale_index)
             {
               launch_downscale(oc.G + static_cast<size_t>(s) * oc.layer_stride, oc.w, oc.h, oc.pitch, next->G, next->w,
@@ -421,7 +432,14 @@ namespace {
         }
         if (fused)
         {
+          if (prof && o == 0)
+          {
+            CU(ctx, cudaEventRecord(S.ev[7], st));
+            S.top_kernel_bytes = 48.0 * oc.w * oc.h;  // reads G(0), writes G(1..5) and D(0..4)
+          }
           const int n = launch_fused_octave(oc, next, S.downscale_index, S.stage_taps.data(), P.n_scales, st);
+          if (prof && o == 0)
+            CU(ctx, cudaEventRecord(S.ev[8], st));
           if (n < 0)
             return fail(ctx, SARA_B200_ERR_CUDA, "fused octave kernel could not be launched (tensor map / attributes)");
           S.pyramid_launches += n;
@@ -516,6 +534,11 @@ namespace {
       S.timings = sara_b200_timings{};
       S.timings.upload = ms(0, 1);
       S.timings.pyramid = ms(1, 2);
+      if (S.top_kernel_bytes > 0.)
+      {
+        S.timings.pyramid_top_kernel = ms(7, 8);
+        S.timings.pyramid_top_kernel_mbytes = static_cast<float>(S.top_kernel_bytes * 1e-6);
+      }
       if (S.has_keypoints)
       {
         S.timings.extrema = ms(2, 3);
@@ -623,7 +646,7 @@ int sara_b200_create(int device, const sara_b200_limits* limits, sara_b200_ctx**
   for (Slot& S : ctx->slots)
   {
     cudaError_t err = cudaStreamCreateWithFlags(&S.own_stream, cudaStreamNonBlocking);
-    for (int i = 0; i < 7 && err == cudaSuccess; ++i)
+    for (int i = 0; i < 9 && err == cudaSuccess; ++i)
       err = cudaEventCreate(&S.ev[i]);
     size_t bytes = 0;
     auto take = [&](size_t n) {
