@@ -91,6 +91,9 @@ namespace sb {
   bool launch_stage(const float* src, int src_pitch, float* dst, float* dog, float* nextG, int w, int h,
                     int pitch, int nw, int nh, int npitch, const Taps& taps, cudaStream_t st);
   bool downscale_is_even_sampling(int sw, int sh, int dw, int dh);
+  // All octaves from `first_octave` on in one single-CTA launch (pyramid.cu); 0 if not applicable.
+  int launch_tail_octaves(const PyramidDesc& P, int first_octave, int downscale_index, const Taps* taps,
+                          cudaStream_t st);
 
   struct ExtremaParams
   {

@@ -393,6 +393,16 @@ namespace {
       {
         const OctaveDesc& oc = P.oct[o];
         const OctaveDesc* next = o + 1 < P.n_octaves ? &P.oct[o + 1] : nullptr;
+        // The small octaves at the end of the pyramid run in one single-CTA launch.
+        if (mode != SARA_B200_PYRAMID_GENERIC && o > 0 && oc.w * oc.h <= 4096)
+        {
+          const int n = launch_tail_octaves(P, o, S.downscale_index, S.stage_taps.data(), st);
+          if (n > 0)
+          {
+            S.pyramid_launches += n;
+            break;
+          }
+        }
         if (staged)
         {
           const bool fuse_down = next != nullptr && S.downscale_index >= 1 &&
