@@ -22,7 +22,8 @@ namespace sb {
   {
     float* G;
     float* D;
-    uint8_t* map;   // extremum map, (n_scales - 3) layers of w * h bytes (ImageProcessing/Extrema.hpp)
+    uint8_t* map;   // extremum map, (n_scales - 3) layers of h rows of map_pitch bytes (ImageProcessing/Extrema.hpp)
+    int map_pitch;  // multiple of 16 >= w
     int* row_count; // (n_scales - 3) * h ints: candidates per raster row
     int w, h, pitch;
     int layer_stride;

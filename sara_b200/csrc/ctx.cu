@@ -237,7 +237,7 @@ namespace {
       const size_t layer = sizeof(float) * pitch[o] * g.oh[o];
       off_G[o] = take(layer * n_s);
       off_D[o] = take(layer * std::max(n_s - 1, 1));
-      off_map[o] = take(static_cast<size_t>(g.ow[o]) * g.oh[o] * std::max(n_ext_layers, 1));
+      off_map[o] = take(align_up(g.ow[o], 16) * g.oh[o] * std::max(n_ext_layers, 1));
       n_seg += n_ext_layers * g.oh[o];
     }
     const size_t off_rows = take(sizeof(int) * std::max(n_seg, 1));
@@ -279,6 +279,7 @@ namespace {
       oc.G = reinterpret_cast<float*>(S.arena + off_G[o]);
       oc.D = reinterpret_cast<float*>(S.arena + off_D[o]);
       oc.map = reinterpret_cast<uint8_t*>(S.arena + off_map[o]);
+      oc.map_pitch = static_cast<int>(align_up(g.ow[o], 16));
       oc.row_count = reinterpret_cast<int*>(S.arena + off_rows) + seg_base;
       oc.w = g.ow[o];
       oc.h = g.oh[o];

@@ -25,81 +25,109 @@ namespace sb {
     }
 
     // ---- pass 1: classify every pixel of D(s, o), s = 1 .. n_scales - 3 ------
-    __global__ void __launch_bounds__(256)
-        classify_kernel(const OctaveDesc oct, const ExtremaParams ep)
+    // LocalScaleSpaceExtremum + threshold + on_edge for one pixel whose value passed the
+    // threshold (RefineExtremum.cpp:407-437).  Returns the uint8 map value.
+    __device__ __forceinline__ uint8_t classify_pixel(const float* __restrict__ Dc, int layer_stride, int pitch, int x,
+                                                      int y, float v, float edge_ratio)
     {
-      const int x = blockIdx.x * 32 + threadIdx.x;
-      const int y = blockIdx.y * 8 + threadIdx.y;
-      const int s = blockIdx.z + 1;
+      // The 8 neighbours of the same layer decide for most pixels, so they go first and the
+      // two adjacent layers are only touched by pixels that are still candidates.
+      bool is_max = true, is_min = true;
+#pragma unroll
+      for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx)
+          if (dx != 0 || dy != 0)
+          {
+            const float cc = ld(Dc, pitch, x + dx, y + dy);
+            is_max = is_max && (v >= cc);
+            is_min = is_min && (v <= cc);
+          }
+      if (!(is_max || is_min))
+        return 0;
+      const float* Dp = Dc - layer_stride;
+      const float* Dn = Dc + layer_stride;
+#pragma unroll
+      for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx)
+        {
+          const float a = ld(Dp, pitch, x + dx, y + dy);
+          const float b = ld(Dn, pitch, x + dx, y + dy);
+          is_max = is_max && (v >= a) && (v >= b);
+          is_min = is_min && (v <= a) && (v <= b);
+        }
+      if (!(is_max || is_min))
+        return 0;
+      // on_edge(): Hessian functor, ImageProcessing/Differential.hpp:191-226.
+      const float c2 = __fmul_rn(2.f, v);
+      const float hxx = __fadd_rn(__fsub_rn(ld(Dc, pitch, x + 1, y), c2), ld(Dc, pitch, x - 1, y));
+      const float hyy = __fadd_rn(__fsub_rn(ld(Dc, pitch, x, y + 1), c2), ld(Dc, pitch, x, y - 1));
+      const float hxy = __fdiv_rn(
+          __fadd_rn(__fsub_rn(__fsub_rn(ld(Dc, pitch, x + 1, y + 1), ld(Dc, pitch, x - 1, y + 1)),
+                              ld(Dc, pitch, x + 1, y - 1)),
+                    ld(Dc, pitch, x - 1, y - 1)),
+          4.f);
+      const float tr = __fadd_rn(hxx, hyy);
+      const float det = __fsub_rn(__fmul_rn(hxx, hyy), __fmul_rn(hxy, hxy));
+      const float e1 = __fadd_rn(edge_ratio, 1.f);
+      const bool edge = __fmul_rn(__fmul_rn(tr, tr), edge_ratio) >= __fmul_rn(__fmul_rn(e1, e1), fabsf(det));
+      if (edge)
+        return 0;
+      return is_max ? 1 : 255;  // maximum is tested first (RefineExtremum.cpp:419-426)
+    }
+
+    // All octaves and scales in one launch.  A block is a tile of 128 x 8 pixels of one DoG
+    // layer: a thread takes 4 consecutive pixels (one float4 of centre values, one uchar4 of
+    // map), a warp is one raster row of the tile and adds its candidates to the row counter.
+    struct ClassifyTiles
+    {
+      int base[kMaxOctaves + 1];  // first tile of every octave
+      int tiles_x[kMaxOctaves], tiles_y[kMaxOctaves];
+    };
+
+    __global__ void __launch_bounds__(256)
+        classify_kernel(const __grid_constant__ PyramidDesc P, const __grid_constant__ ClassifyTiles T,
+                        const ExtremaParams ep)
+    {
+      int o = 0;
+      while (o + 1 < P.n_octaves && static_cast<int>(blockIdx.x) >= T.base[o + 1])
+        ++o;
+      const OctaveDesc& oct = P.oct[o];
+      int tile = blockIdx.x - T.base[o];
+      const int per_layer = T.tiles_x[o] * T.tiles_y[o];
+      const int s = tile / per_layer + 1;
+      tile -= (s - 1) * per_layer;
+      const int ty = tile / T.tiles_x[o], tx = tile - ty * T.tiles_x[o];
+      const int x0 = (tx * 32 + threadIdx.x) * 4;
+      const int y = ty * 8 + threadIdx.y;
       const int w = oct.w, h = oct.h, pitch = oct.pitch;
       if (y >= h)
         return;
-      uint8_t type = 0;
-      const bool in_domain = x < w && ep.pad <= x && x < w - ep.pad && ep.pad <= y && y < h - ep.pad;
-      if (in_domain)
+      uchar4 types = make_uchar4(0, 0, 0, 0);
+      const float thr = __fmul_rn(0.8f, ep.extremum_thres);
+      if (x0 < w && ep.pad <= y && y < h - ep.pad)
       {
         const float* Dc = oct.D + static_cast<size_t>(s) * oct.layer_stride;
-        const float v = ld(Dc, pitch, x, y);
-        // All three rejections are ANDed in the reference; the cheap threshold
-        // test goes first.
-        if (!(fabsf(v) < __fmul_rn(0.8f, ep.extremum_thres)))
+        const float4 v4 = __ldg(reinterpret_cast<const float4*>(Dc + static_cast<size_t>(y) * pitch + x0));
+        const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+        uint8_t t[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
         {
-          // LocalScaleSpaceExtremum (Extrema.hpp:63-75): v >= (<=) all 26 neighbours.  The 8
-          // neighbours of the same layer decide for most pixels, so they go first and the
-          // two adjacent layers are only touched by pixels that are still candidates.
-          bool is_max = true, is_min = true;
-#pragma unroll
-          for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-            for (int dx = -1; dx <= 1; ++dx)
-              if (dx != 0 || dy != 0)
-              {
-                const float cc = ld(Dc, pitch, x + dx, y + dy);
-                is_max = is_max && (v >= cc);
-                is_min = is_min && (v <= cc);
-              }
-          if (is_max || is_min)
-          {
-            const float* Dp = Dc - oct.layer_stride;
-            const float* Dn = Dc + oct.layer_stride;
-#pragma unroll
-            for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-              for (int dx = -1; dx <= 1; ++dx)
-              {
-                const float a = ld(Dp, pitch, x + dx, y + dy);
-                const float b = ld(Dn, pitch, x + dx, y + dy);
-                is_max = is_max && (v >= a) && (v >= b);
-                is_min = is_min && (v <= a) && (v <= b);
-              }
-          }
-          if (is_max || is_min)
-          {
-            // on_edge(): Hessian functor, ImageProcessing/Differential.hpp:191-226.
-            const float c2 = __fmul_rn(2.f, v);
-            const float hxx = __fadd_rn(__fsub_rn(ld(Dc, pitch, x + 1, y), c2), ld(Dc, pitch, x - 1, y));
-            const float hyy = __fadd_rn(__fsub_rn(ld(Dc, pitch, x, y + 1), c2), ld(Dc, pitch, x, y - 1));
-            const float hxy =
-                __fdiv_rn(__fadd_rn(__fsub_rn(__fsub_rn(ld(Dc, pitch, x + 1, y + 1),
-                                                        ld(Dc, pitch, x - 1, y + 1)),
-                                              ld(Dc, pitch, x + 1, y - 1)),
-                                    ld(Dc, pitch, x - 1, y - 1)),
-                          4.f);
-            const float tr = __fadd_rn(hxx, hyy);
-            const float det = __fsub_rn(__fmul_rn(hxx, hyy), __fmul_rn(hxy, hxy));
-            const float e1 = __fadd_rn(ep.edge_ratio, 1.f);
-            const bool edge =
-                __fmul_rn(__fmul_rn(tr, tr), ep.edge_ratio) >= __fmul_rn(__fmul_rn(e1, e1), fabsf(det));
-            if (!edge)
-              type = is_max ? 1 : 255;  // maximum is tested first (RefineExtremum.cpp:419-426)
-          }
+          const int x = x0 + e;
+          // all the rejections are ANDed in the reference; the cheap threshold test goes first
+          if (ep.pad <= x && x < w - ep.pad && !(fabsf(v[e]) < thr))
+            t[e] = classify_pixel(Dc, oct.layer_stride, pitch, x, y, v[e], ep.edge_ratio);
         }
+        types = make_uchar4(t[0], t[1], t[2], t[3]);
       }
-      if (x < w)
-        oct.map[(static_cast<size_t>(s - 1) * h + y) * w + x] = type;
-      const unsigned m = __ballot_sync(0xffffffffu, type != 0);
-      if (threadIdx.x == 0 && m != 0)
-        atomicAdd(oct.row_count + (s - 1) * h + y, __popc(m));
+      if (x0 < oct.map_pitch)
+        *reinterpret_cast<uchar4*>(oct.map + (static_cast<size_t>(s - 1) * h + y) * oct.map_pitch + x0) = types;
+      const int mine = (types.x != 0) + (types.y != 0) + (types.z != 0) + (types.w != 0);
+      const int total = __reduce_add_sync(0xffffffffu, mine);
+      if (threadIdx.x == 0 && total != 0)
+        atomicAdd(oct.row_count + (s - 1) * h + y, total);
     }
 
     // ---- ordered compaction: one warp per raster row -------------------------
@@ -123,7 +151,7 @@ namespace sb {
         if (oc.row_count[r] == 0)
           continue;
         int out = seg_off[seg] + seg_chunk_off[seg >> 10];
-        const uint8_t* row = oc.map + (static_cast<size_t>(s - 1) * oc.h + y) * oc.w;
+        const uint8_t* row = oc.map + (static_cast<size_t>(s - 1) * oc.h + y) * oc.map_pitch;
         // The map is almost empty: scan it 4 bytes per lane (128 pixels per warp step) and
         // only expand the words that hold a candidate.  Order inside a row = x order.
         const int w = oc.w;
@@ -435,11 +463,16 @@ namespace sb {
     const int n_s = P.n_scales - 3;
     // row counts of all octaves are contiguous, starting at octave 0's.
     cudaMemsetAsync(P.oct[0].row_count, 0, sizeof(int) * n_segments, st);
+    ClassifyTiles T{};
     for (int o = 0; o < P.n_octaves; ++o)
     {
-      const OctaveDesc& oc = P.oct[o];
-      dim3 grid((oc.w + 31) / 32, (oc.h + 7) / 8, n_s);
-      classify_kernel<<<grid, dim3(32, 8), 0, st>>>(oc, ep);
+      T.tiles_x[o] = (P.oct[o].w + 127) / 128;
+      T.tiles_y[o] = (P.oct[o].h + 7) / 8;
+      T.base[o + 1] = T.base[o] + T.tiles_x[o] * T.tiles_y[o] * n_s;
+    }
+    if (T.base[P.n_octaves] > 0)
+    {
+      classify_kernel<<<T.base[P.n_octaves], dim3(32, 8), 0, st>>>(P, T, ep);
       ++launches;
     }
     // scratch layout: [chunk offsets (1024)] [keep flags cap_cand] [flag offsets cap_cand]
