@@ -278,6 +278,11 @@ namespace sb {
         {
           float fu, fv, xn, xp, yn, yp;
         };
+        // Keypoints whose whole window (plus the gradient stencil) lies inside the layer skip
+        // the one-sided border differences of the Gradient functor (Differential.hpp:46-61).
+        const bool interior = rx - rounded_r >= 1 && rx + rounded_r <= w - 2 && ry - rounded_r >= 1 &&
+                              ry + rounded_r <= h - 2;
+        const float* Gc = G + static_cast<size_t>(ry) * pitch + rx;
         auto fetch = [&](int uv, bool on) {
           Sample sm;
           const int u = static_cast<short>(uv & 0xffff), v = uv >> 16;
@@ -286,15 +291,25 @@ namespace sb {
           sm.xn = sm.xp = sm.yn = sm.yp = 0.f;
           if (on)
           {
-            // gradient_polar_coordinates on the fly, one-sided differences at the borders
-            const int X = rx + u, Y = ry + v;
-            const float* row = G + static_cast<size_t>(Y) * pitch;
-            const int xn = X == w - 1 ? X : X + 1, xp = X == 0 ? X : X - 1;
-            const int yn = Y == h - 1 ? Y : Y + 1, yp = Y == 0 ? Y : Y - 1;
-            sm.xn = __ldg(row + xn);
-            sm.xp = __ldg(row + xp);
-            sm.yn = __ldg(G + static_cast<size_t>(yn) * pitch + X);
-            sm.yp = __ldg(G + static_cast<size_t>(yp) * pitch + X);
+            if (interior)
+            {
+              const float* p = Gc + (v * pitch + u);
+              sm.xn = __ldg(p + 1);
+              sm.xp = __ldg(p - 1);
+              sm.yn = __ldg(p + pitch);
+              sm.yp = __ldg(p - pitch);
+            }
+            else
+            {
+              const int X = rx + u, Y = ry + v;
+              const float* row = G + static_cast<size_t>(Y) * pitch;
+              const int xn = X == w - 1 ? X : X + 1, xp = X == 0 ? X : X - 1;
+              const int yn = Y == h - 1 ? Y : Y + 1, yp = Y == 0 ? Y : Y - 1;
+              sm.xn = __ldg(row + xn);
+              sm.xp = __ldg(row + xp);
+              sm.yn = __ldg(G + static_cast<size_t>(yn) * pitch + X);
+              sm.yp = __ldg(G + static_cast<size_t>(yp) * pitch + X);
+            }
           }
           return sm;
         };
@@ -311,31 +326,40 @@ namespace sb {
           float ori = __fsub_rn(fast_atan2(dy, dx), theta);
           ori = ori < 0.f ? __fadd_rn(ori, kTwoPi) : ori;
           ori = __fmul_rn(ori, 1.27323954f);  // 8 / (2 pi)
-          // std::modf truncates toward zero (quirk N6)
-          const float xif = truncf(px), yif = truncf(py), oif = truncf(ori);
-          const float xfrac = __fsub_rn(px, xif), yfrac = __fsub_rn(py, yif), ofrac = __fsub_rn(ori, oif);
-          const int xi = static_cast<int>(xif), yi = static_cast<int>(yif), oi = static_cast<int>(oif);
+          // std::modf truncates toward zero (quirk N6): for pos in (-1, 0) the integer part is 0,
+          // the weight of cell 0 is 1 - frac > 1 and the one of cell 1 is frac < 0.
+          const int xi = static_cast<int>(px), yi = static_cast<int>(py), oi = static_cast<int>(ori);
+          const float xfrac = __fsub_rn(px, static_cast<float>(xi)), yfrac = __fsub_rn(py, static_cast<float>(yi));
+          const float ofrac = __fsub_rn(ori, static_cast<float>(oi));
           const float wm = __fmul_rn(weight, mag);
           const float wo1 = __fmul_rn(ofrac, wm), wo0 = __fsub_rn(wm, wo1);
-          const int o0 = oi & 7, o1 = (oi + 1) & 7;
-#pragma unroll
-          for (int dyy = 0; dyy < 2; ++dyy)
+          // (xi, yi) in [0, 3]; the +1 neighbours exist for xi, yi < 3
+          const float wy0 = __fsub_rn(1.f, yfrac), wx0 = __fsub_rn(1.f, xfrac);
+          const bool x1 = xi < 3, y1 = yi < 3;
+          float* cell = priv + ((4 * yi + xi) * 8) * 32 + lane;
+          const int o0 = (oi & 7) * 32, o1 = ((oi + 1) & 7) * 32;
           {
-            const int yy = yi + dyy;
-            if (yy < 0 || yy >= 4)
-              continue;
-            const float wy = dyy == 0 ? __fsub_rn(1.f, yfrac) : yfrac;
-#pragma unroll
-            for (int dxx = 0; dxx < 2; ++dxx)
-            {
-              const int xx = xi + dxx;
-              if (xx < 0 || xx >= 4)
-                continue;
-              const float wxy = __fmul_rn(wy, dxx == 0 ? __fsub_rn(1.f, xfrac) : xfrac);
-              float* cell = priv + (32 * yy + 8 * xx) * 32 + lane;
-              cell[o0 * 32] = __fadd_rn(cell[o0 * 32], __fmul_rn(wxy, wo0));
-              cell[o1 * 32] = __fadd_rn(cell[o1 * 32], __fmul_rn(wxy, wo1));
-            }
+            const float a = __fmul_rn(wy0, wx0);
+            cell[o0] = __fadd_rn(cell[o0], __fmul_rn(a, wo0));
+            cell[o1] = __fadd_rn(cell[o1], __fmul_rn(a, wo1));
+          }
+          if (x1)
+          {
+            const float a = __fmul_rn(wy0, xfrac);
+            cell[256 + o0] = __fadd_rn(cell[256 + o0], __fmul_rn(a, wo0));
+            cell[256 + o1] = __fadd_rn(cell[256 + o1], __fmul_rn(a, wo1));
+          }
+          if (y1)
+          {
+            const float a = __fmul_rn(yfrac, wx0);
+            cell[1024 + o0] = __fadd_rn(cell[1024 + o0], __fmul_rn(a, wo0));
+            cell[1024 + o1] = __fadd_rn(cell[1024 + o1], __fmul_rn(a, wo1));
+          }
+          if (x1 && y1)
+          {
+            const float a = __fmul_rn(yfrac, xfrac);
+            cell[1280 + o0] = __fadd_rn(cell[1280 + o0], __fmul_rn(a, wo0));
+            cell[1280 + o1] = __fadd_rn(cell[1280 + o1], __fmul_rn(a, wo1));
           }
         };
         // Processes queue entries [0, m), m <= 96, three per lane with their loads overlapped.

@@ -77,7 +77,7 @@ namespace sb {
       return is_max ? 1 : 255;  // maximum is tested first (RefineExtremum.cpp:419-426)
     }
 
-    // All octaves and scales in one launch.  A block is a tile of 128 x 8 pixels of one DoG
+    // All octaves and scales in one launch.  A block is a tile of 128 x 32 pixels of one DoG
     // layer: a thread takes 4 consecutive pixels (one float4 of centre values, one uchar4 of
     // map), a warp is one raster row of the tile and adds its candidates to the row counter.
     struct ClassifyTiles
@@ -100,34 +100,49 @@ namespace sb {
       tile -= (s - 1) * per_layer;
       const int ty = tile / T.tiles_x[o], tx = tile - ty * T.tiles_x[o];
       const int x0 = (tx * 32 + threadIdx.x) * 4;
-      const int y = ty * 8 + threadIdx.y;
       const int w = oct.w, h = oct.h, pitch = oct.pitch;
-      if (y >= h)
-        return;
-      uchar4 types = make_uchar4(0, 0, 0, 0);
       const float thr = __fmul_rn(0.8f, ep.extremum_thres);
-      if (x0 < w && ep.pad <= y && y < h - ep.pad)
-      {
-        const float* Dc = oct.D + static_cast<size_t>(s) * oct.layer_stride;
-        const float4 v4 = __ldg(reinterpret_cast<const float4*>(Dc + static_cast<size_t>(y) * pitch + x0));
-        const float v[4] = {v4.x, v4.y, v4.z, v4.w};
-        uint8_t t[4] = {0, 0, 0, 0};
+      const float* Dc = oct.D + static_cast<size_t>(s) * oct.layer_stride;
+      // four rows per thread: their centre values are requested together
+      float4 v4[4];
+      bool row_on[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-        {
-          const int x = x0 + e;
-          // all the rejections are ANDed in the reference; the cheap threshold test goes first
-          if (ep.pad <= x && x < w - ep.pad && !(fabsf(v[e]) < thr))
-            t[e] = classify_pixel(Dc, oct.layer_stride, pitch, x, y, v[e], ep.edge_ratio);
-        }
-        types = make_uchar4(t[0], t[1], t[2], t[3]);
+      for (int k = 0; k < 4; ++k)
+      {
+        const int y = ty * 32 + threadIdx.y + 8 * k;
+        row_on[k] = x0 < w && ep.pad <= y && y < h - ep.pad;
+        v4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row_on[k])
+          v4[k] = __ldg(reinterpret_cast<const float4*>(Dc + static_cast<size_t>(y) * pitch + x0));
       }
-      if (x0 < oct.map_pitch)
-        *reinterpret_cast<uchar4*>(oct.map + (static_cast<size_t>(s - 1) * h + y) * oct.map_pitch + x0) = types;
-      const int mine = (types.x != 0) + (types.y != 0) + (types.z != 0) + (types.w != 0);
-      const int total = __reduce_add_sync(0xffffffffu, mine);
-      if (threadIdx.x == 0 && total != 0)
-        atomicAdd(oct.row_count + (s - 1) * h + y, total);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+      {
+        const int y = ty * 32 + threadIdx.y + 8 * k;
+        if (y >= h)
+          break;  // warp-uniform: a warp is one row
+        uchar4 types = make_uchar4(0, 0, 0, 0);
+        if (row_on[k])
+        {
+          const float v[4] = {v4[k].x, v4[k].y, v4[k].z, v4[k].w};
+          uint8_t t[4] = {0, 0, 0, 0};
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+          {
+            const int x = x0 + e;
+            // all the rejections are ANDed in the reference; the cheap threshold test goes first
+            if (ep.pad <= x && x < w - ep.pad && !(fabsf(v[e]) < thr))
+              t[e] = classify_pixel(Dc, oct.layer_stride, pitch, x, y, v[e], ep.edge_ratio);
+          }
+          types = make_uchar4(t[0], t[1], t[2], t[3]);
+        }
+        if (x0 < oct.map_pitch)
+          *reinterpret_cast<uchar4*>(oct.map + (static_cast<size_t>(s - 1) * h + y) * oct.map_pitch + x0) = types;
+        const int mine = (types.x != 0) + (types.y != 0) + (types.z != 0) + (types.w != 0);
+        const int total = __reduce_add_sync(0xffffffffu, mine);
+        if (threadIdx.x == 0 && total != 0)
+          atomicAdd(oct.row_count + (s - 1) * h + y, total);
+      }
     }
 
     // ---- ordered compaction: one warp per raster row -------------------------
@@ -158,41 +173,53 @@ namespace sb {
         const int mis = static_cast<int>(reinterpret_cast<uintptr_t>(row) & 3u);  // row start inside its 4-byte word
         const uint32_t* words = reinterpret_cast<const uint32_t*>(row - mis);
         const int n_words = (mis + w + 3) >> 2;
-        for (int w0 = 0; w0 < n_words; w0 += 32)
+        for (int w00 = 0; w00 < n_words; w00 += 128)
         {
-          const int wi = w0 + lane;
-          uint32_t v = wi < n_words ? __ldg(words + wi) : 0u;
-          // mask bytes outside [row, row + w)
-          const int x_first = 4 * wi - mis;
+          uint32_t vv[4];
 #pragma unroll
-          for (int b = 0; b < 4; ++b)
-            if (x_first + b < 0 || x_first + b >= w)
-              v &= ~(0xffu << (8 * b));
-          const int mine = (v & 0xffu ? 1 : 0) + (v & 0xff00u ? 1 : 0) + (v & 0xff0000u ? 1 : 0) + (v >> 24 ? 1 : 0);
-          if (__ballot_sync(0xffffffffu, mine != 0) == 0u)
-            continue;
-          // exclusive prefix of `mine` across the warp
-          int inc = mine;
-#pragma unroll
-          for (int d = 1; d < 32; d <<= 1)
+          for (int k = 0; k < 4; ++k)  // four 128-pixel steps requested together
           {
-            const int t = __shfl_up_sync(0xffffffffu, inc, d);
-            if (lane >= d)
-              inc += t;
+            const int wi = w00 + 32 * k + lane;
+            vv[k] = wi < n_words ? __ldg(words + wi) : 0u;
           }
-          int pos = out + inc - mine;
 #pragma unroll
-          for (int b = 0; b < 4; ++b)
+          for (int k = 0; k < 4; ++k)
           {
-            const uint32_t t = (v >> (8 * b)) & 0xffu;
-            if (t != 0)
+            const int wi = w00 + 32 * k + lane;
+            uint32_t v = vv[k];
+            // mask bytes outside [row, row + w)
+            const int x_first = 4 * wi - mis;
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+              if (x_first + b < 0 || x_first + b >= w)
+                v &= ~(0xffu << (8 * b));
+            const int mine =
+                (v & 0xffu ? 1 : 0) + (v & 0xff00u ? 1 : 0) + (v & 0xff0000u ? 1 : 0) + (v >> 24 ? 1 : 0);
+            if (__ballot_sync(0xffffffffu, mine != 0) == 0u)
+              continue;
+            // exclusive prefix of `mine` across the warp
+            int inc = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1)
             {
-              if (pos < cap_cand)
-                cand[pos] = Candidate{x_first + b, y, (o << 8) | s, static_cast<int>(t)};
-              ++pos;
+              const int t = __shfl_up_sync(0xffffffffu, inc, d);
+              if (lane >= d)
+                inc += t;
             }
+            int pos = out + inc - mine;
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+            {
+              const uint32_t t = (v >> (8 * b)) & 0xffu;
+              if (t != 0)
+              {
+                if (pos < cap_cand)
+                  cand[pos] = Candidate{x_first + b, y, (o << 8) | s, static_cast<int>(t)};
+                ++pos;
+              }
+            }
+            out += __shfl_sync(0xffffffffu, inc, 31);
           }
-          out += __shfl_sync(0xffffffffu, inc, 31);
         }
       }
     }
@@ -467,7 +494,7 @@ namespace sb {
     for (int o = 0; o < P.n_octaves; ++o)
     {
       T.tiles_x[o] = (P.oct[o].w + 127) / 128;
-      T.tiles_y[o] = (P.oct[o].h + 7) / 8;
+      T.tiles_y[o] = (P.oct[o].h + 31) / 32;
       T.base[o + 1] = T.base[o] + T.tiles_x[o] * T.tiles_y[o] * n_s;
     }
     if (T.base[P.n_octaves] > 0)
