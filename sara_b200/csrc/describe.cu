@@ -233,10 +233,12 @@ namespace sb {
                           Counters* __restrict__ counters, int cap_kp, Keypoint* __restrict__ kp_out,
                           float* __restrict__ desc)
     {
-      extern __shared__ float s_dyn[];  // DESC_WARPS x (128 x 32 lane-private bins + 128 queue entries)
+      extern __shared__ float s_dyn[];  // DESC_WARPS x (128 bins x 16 copies + 128 queue entries)
       const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-      float* priv = s_dyn + wid * (128 * 32 + 128);
-      int* queue = reinterpret_cast<int*>(priv + 128 * 32);
+      float* priv = s_dyn + wid * (128 * 16 + 128);
+      int* queue = reinterpret_cast<int*>(priv + 128 * 16);
+      const int l16 = lane & 15;
+      const bool lo_half = lane < 16;
       const int n = min(counters->n_kp, cap_kp);
 
       while (true)
@@ -267,8 +269,10 @@ namespace sb {
         const int rx = static_cast<int>(roundf(kp.x));
         const int ry = static_cast<int>(roundf(kp.y));
 
+        // Histogram: 16 copies of the 128 bins; lanes l and l + 16 share copy l and update it
+        // in two separate phases (fixed order => deterministic sums, no bank conflicts).
 #pragma unroll 8
-        for (int b = 0; b < 128; ++b)
+        for (int b = 0; b < 64; ++b)
           priv[b * 32 + lane] = 0.f;
 
         // A kept sample in two steps, so that the loads of several samples are in flight
@@ -313,9 +317,14 @@ namespace sb {
           }
           return sm;
         };
-        auto finish = [&](const Sample& sm, bool on) {
-          if (!on)
-            return;
+        struct Weights
+        {
+          int cell, o0, o1;
+          float a00, a01, a10, a11, wo0, wo1;
+          bool x1, y1;
+        };
+        auto weights = [&](const Sample& sm) {
+          Weights w;
           float px = __fadd_rn(__fmul_rn(T00, sm.fu), __fmul_rn(T01, sm.fv));
           float py = __fadd_rn(__fmul_rn(T10, sm.fu), __fmul_rn(T11, sm.fv));
           const float weight = __expf(__fmul_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), -0.125f));
@@ -336,30 +345,40 @@ namespace sb {
           // (xi, yi) in [0, 3]; the +1 neighbours exist for xi, yi < 3
           const float wy0 = __fsub_rn(1.f, yfrac), wx0 = __fsub_rn(1.f, xfrac);
           const bool x1 = xi < 3, y1 = yi < 3;
-          float* cell = priv + ((4 * yi + xi) * 8) * 32 + lane;
-          const int o0 = (oi & 7) * 32, o1 = ((oi + 1) & 7) * 32;
+          w.cell = ((4 * yi + xi) * 8) * 16 + l16;
+          w.o0 = (oi & 7) * 16;
+          w.o1 = ((oi + 1) & 7) * 16;
+          w.a00 = __fmul_rn(wy0, wx0);
+          w.a01 = x1 ? __fmul_rn(wy0, xfrac) : 0.f;
+          w.a10 = y1 ? __fmul_rn(yfrac, wx0) : 0.f;
+          w.a11 = (x1 && y1) ? __fmul_rn(yfrac, xfrac) : 0.f;
+          w.x1 = x1;
+          w.y1 = y1;
+          w.wo0 = wo0;
+          w.wo1 = wo1;
+          return w;
+        };
+        // the 8 bin updates of one sample for the lanes of one half-warp
+        auto update = [&](const Weights& w, bool mine) {
+          if (!mine)
+            return;
+          float* cell = priv + w.cell;
+          cell[w.o0] = __fadd_rn(cell[w.o0], __fmul_rn(w.a00, w.wo0));
+          cell[w.o1] = __fadd_rn(cell[w.o1], __fmul_rn(w.a00, w.wo1));
+          if (w.x1)
           {
-            const float a = __fmul_rn(wy0, wx0);
-            cell[o0] = __fadd_rn(cell[o0], __fmul_rn(a, wo0));
-            cell[o1] = __fadd_rn(cell[o1], __fmul_rn(a, wo1));
+            cell[128 + w.o0] = __fadd_rn(cell[128 + w.o0], __fmul_rn(w.a01, w.wo0));
+            cell[128 + w.o1] = __fadd_rn(cell[128 + w.o1], __fmul_rn(w.a01, w.wo1));
           }
-          if (x1)
+          if (w.y1)
           {
-            const float a = __fmul_rn(wy0, xfrac);
-            cell[256 + o0] = __fadd_rn(cell[256 + o0], __fmul_rn(a, wo0));
-            cell[256 + o1] = __fadd_rn(cell[256 + o1], __fmul_rn(a, wo1));
+            cell[512 + w.o0] = __fadd_rn(cell[512 + w.o0], __fmul_rn(w.a10, w.wo0));
+            cell[512 + w.o1] = __fadd_rn(cell[512 + w.o1], __fmul_rn(w.a10, w.wo1));
           }
-          if (y1)
+          if (w.x1 && w.y1)
           {
-            const float a = __fmul_rn(yfrac, wx0);
-            cell[1024 + o0] = __fadd_rn(cell[1024 + o0], __fmul_rn(a, wo0));
-            cell[1024 + o1] = __fadd_rn(cell[1024 + o1], __fmul_rn(a, wo1));
-          }
-          if (x1 && y1)
-          {
-            const float a = __fmul_rn(yfrac, xfrac);
-            cell[1280 + o0] = __fadd_rn(cell[1280 + o0], __fmul_rn(a, wo0));
-            cell[1280 + o1] = __fadd_rn(cell[1280 + o1], __fmul_rn(a, wo1));
+            cell[640 + w.o0] = __fadd_rn(cell[640 + w.o0], __fmul_rn(w.a11, w.wo0));
+            cell[640 + w.o1] = __fadd_rn(cell[640 + w.o1], __fmul_rn(w.a11, w.wo1));
           }
         };
         // Processes queue entries [0, m), m <= 96, three per lane with their loads overlapped.
@@ -368,14 +387,22 @@ namespace sb {
           const Sample a = fetch(queue[lane], on0);
           const Sample b = fetch(queue[lane + 32], on1);
           const Sample c = fetch(queue[lane + 64], on2);
-          finish(a, on0);
-          finish(b, on1);
-          finish(c, on2);
+          const Weights wa = weights(a), wb = weights(b), wc = weights(c);
+          update(wa, on0 && lo_half);
+          update(wb, on1 && lo_half);
+          update(wc, on2 && lo_half);
+          __syncwarp();
+          update(wa, on0 && !lo_half);
+          update(wb, on1 && !lo_half);
+          update(wc, on2 && !lo_half);
+          __syncwarp();
         };
 
         const int side = 2 * rounded_r + 1;
         const int count = side * side;
         int q_n = 0;  // entries waiting in the queue (< 96 between rounds)
+        // lane's pixel of the bounding square, advanced by 32 per round (side >= 35 > 32)
+        int u = lane - rounded_r, v = -rounded_r;
         for (int t0 = 0; t0 < count; t0 += 32)
         {
           const int t = t0 + lane;
@@ -383,15 +410,18 @@ namespace sb {
           int uv = 0;
           if (t < count)
           {
-            const int vv = t / side;
-            const int v = vv - rounded_r;
-            const int u = t - vv * side - rounded_r;
             const int X = rx + u, Y = ry + v;
             const float fu = static_cast<float>(u), fv = static_cast<float>(v);
             const float px = __fadd_rn(__fadd_rn(__fmul_rn(T00, fu), __fmul_rn(T01, fv)), 1.5f);
             const float py = __fadd_rn(__fadd_rn(__fmul_rn(T10, fu), __fmul_rn(T11, fv)), 1.5f);
             keep = X >= 0 && X < w && Y >= 0 && Y < h && fminf(px, py) > -1.f && fmaxf(px, py) < 4.f;
             uv = (u & 0xffff) | (v << 16);
+          }
+          u += 32;
+          if (u > rounded_r)
+          {
+            u -= side;
+            ++v;
           }
           const unsigned m = __ballot_sync(0xffffffffu, keep);
           if (keep)
@@ -419,11 +449,11 @@ namespace sb {
 #pragma unroll
         for (int q = 0; q < 4; ++q)
         {
-          const float* pb = priv + (q * 32 + lane) * 32;
+          const float* pb = priv + (q * 32 + lane) * 16;
           float sum = 0.f;
 #pragma unroll 8
-          for (int j = 0; j < 32; ++j)
-            sum = __fadd_rn(sum, pb[(j + lane) & 31]);
+          for (int j = 0; j < 16; ++j)
+            sum = __fadd_rn(sum, pb[(j + lane) & 15]);
           hv[q] = sum;
         }
         __syncwarp();
@@ -487,9 +517,9 @@ namespace sb {
   int launch_descriptors(const PyramidDesc& P, const Keypoint* kp_oct, Keypoint* kp_out, float* desc,
                          int cap_kp, Counters* counters, cudaStream_t st)
   {
-    const int smem = DESC_WARPS * (128 * 32 + 128) * sizeof(float);
+    const int smem = DESC_WARPS * (128 * 16 + 128) * sizeof(float);
     cudaFuncSetAttribute(descriptor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    descriptor_kernel<<<148 * 3, DESC_WARPS * 32, smem, st>>>(P, kp_oct, counters, cap_kp, kp_out, desc);
+    descriptor_kernel<<<148 * 6, DESC_WARPS * 32, smem, st>>>(P, kp_oct, counters, cap_kp, kp_out, desc);
     return 1;
   }
 
