@@ -99,3 +99,35 @@ def test_product_does_not_touch_oracle():
                 assert not re.search(r"^\s*(from|import)\s+oracle|libsara_oracle|sift_oracle", txt, re.M), f
     out = subprocess.check_output(["ldd", sb.library_path()], text=True)
     assert "oracle" not in out
+
+
+def test_pyramid_kernels_keep_multiply_and_add_apart():
+    """The reference's arithmetic is RN(acc + RN(b * k)) per tap.  ptxas contracts
+    mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with --fmad=false
+    (profiles/microbench), which would change the bits; the kernels issue the add as
+    acc * ONE + p instead.  Check in the SASS that every packed multiply kept its own
+    packed add, and that the TMA path is really there."""
+    import shutil
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.check_output([cuobjdump, "-sass", sb.library_path()], text=True)
+    per_kernel, cur = {}, None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = per_kernel.setdefault(m.group(1), {"FMUL2": 0, "FFMA2": 0, "UTMALDG": 0, "FFMA": 0})
+            continue
+        if cur is None:
+            continue
+        m = re.match(r"\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", line)
+        if m and m.group(1) in cur:
+            cur[m.group(1)] += 1
+    tma = [k for k in per_kernel if "stage_kernel" in k or "fused_octave_kernel" in k]
+    assert len(tma) >= 7
+    for k in tma:
+        c = per_kernel[k]
+        assert c["UTMALDG"] >= 1, k
+        assert c["FMUL2"] > 0 and c["FMUL2"] == c["FFMA2"], (k, c)
+        assert c["FFMA"] == 0, (k, c)  # no scalar contraction either
