@@ -124,7 +124,7 @@ def test_pyramid_kernels_keep_multiply_and_add_apart():
         m = re.match(r"\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", line)
         if m and m.group(1) in cur:
             cur[m.group(1)] += 1
-    tma = [k for k in per_kernel if "stage_kernel" in k or "fused_octave_kernel" in k]
+    tma = [k for k in per_kernel if "5stage12stage_kernel" in k or "fused_octave_kernel" in k]
     assert len(tma) >= 7
     for k in tma:
         c = per_kernel[k]
