@@ -193,6 +193,7 @@ namespace sb {
     }
 
     constexpr int DESC_WARPS = 4;
+    constexpr int DESC_NC = 16;  // copies of the 128-bin histogram per warp; 32 / DESC_NC update phases
 
     // atan2 for the descriptor's soft orientation binning: odd minimax polynomial on [0, 1]
     // (|error| < 1e-5 rad, i.e. 1.3e-5 of a bin; the binning is continuous in the angle, so this
@@ -235,10 +236,10 @@ namespace sb {
     {
       extern __shared__ float s_dyn[];  // DESC_WARPS x (128 bins x 16 copies + 128 queue entries)
       const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-      float* priv = s_dyn + wid * (128 * 16 + 128);
-      int* queue = reinterpret_cast<int*>(priv + 128 * 16);
-      const int l16 = lane & 15;
-      const bool lo_half = lane < 16;
+      float* priv = s_dyn + wid * (128 * DESC_NC + 128);
+      int* queue = reinterpret_cast<int*>(priv + 128 * DESC_NC);
+      const int lcopy = lane & (DESC_NC - 1);
+      const int lphase = lane / DESC_NC;
       const int n = min(counters->n_kp, cap_kp);
 
       while (true)
@@ -269,10 +270,10 @@ namespace sb {
         const int rx = static_cast<int>(roundf(kp.x));
         const int ry = static_cast<int>(roundf(kp.y));
 
-        // Histogram: 16 copies of the 128 bins; lanes l and l + 16 share copy l and update it
-        // in two separate phases (fixed order => deterministic sums, no bank conflicts).
+        // Histogram: DESC_NC copies of the 128 bins; the lanes that share a copy update it in
+        // separate phases (fixed order => deterministic sums, no bank conflicts).
 #pragma unroll 8
-        for (int b = 0; b < 64; ++b)
+        for (int b = 0; b < 4 * DESC_NC; ++b)
           priv[b * 32 + lane] = 0.f;
 
         // A kept sample in two steps, so that the loads of several samples are in flight
@@ -345,9 +346,9 @@ namespace sb {
           // (xi, yi) in [0, 3]; the +1 neighbours exist for xi, yi < 3
           const float wy0 = __fsub_rn(1.f, yfrac), wx0 = __fsub_rn(1.f, xfrac);
           const bool x1 = xi < 3, y1 = yi < 3;
-          w.cell = ((4 * yi + xi) * 8) * 16 + l16;
-          w.o0 = (oi & 7) * 16;
-          w.o1 = ((oi + 1) & 7) * 16;
+          w.cell = ((4 * yi + xi) * 8) * DESC_NC + lcopy;
+          w.o0 = (oi & 7) * DESC_NC;
+          w.o1 = ((oi + 1) & 7) * DESC_NC;
           w.a00 = __fmul_rn(wy0, wx0);
           w.a01 = x1 ? __fmul_rn(wy0, xfrac) : 0.f;
           w.a10 = y1 ? __fmul_rn(yfrac, wx0) : 0.f;
@@ -367,18 +368,18 @@ namespace sb {
           cell[w.o1] = __fadd_rn(cell[w.o1], __fmul_rn(w.a00, w.wo1));
           if (w.x1)
           {
-            cell[128 + w.o0] = __fadd_rn(cell[128 + w.o0], __fmul_rn(w.a01, w.wo0));
-            cell[128 + w.o1] = __fadd_rn(cell[128 + w.o1], __fmul_rn(w.a01, w.wo1));
+            cell[8 * DESC_NC + w.o0] = __fadd_rn(cell[8 * DESC_NC + w.o0], __fmul_rn(w.a01, w.wo0));
+            cell[8 * DESC_NC + w.o1] = __fadd_rn(cell[8 * DESC_NC + w.o1], __fmul_rn(w.a01, w.wo1));
           }
           if (w.y1)
           {
-            cell[512 + w.o0] = __fadd_rn(cell[512 + w.o0], __fmul_rn(w.a10, w.wo0));
-            cell[512 + w.o1] = __fadd_rn(cell[512 + w.o1], __fmul_rn(w.a10, w.wo1));
+            cell[32 * DESC_NC + w.o0] = __fadd_rn(cell[32 * DESC_NC + w.o0], __fmul_rn(w.a10, w.wo0));
+            cell[32 * DESC_NC + w.o1] = __fadd_rn(cell[32 * DESC_NC + w.o1], __fmul_rn(w.a10, w.wo1));
           }
           if (w.x1 && w.y1)
           {
-            cell[640 + w.o0] = __fadd_rn(cell[640 + w.o0], __fmul_rn(w.a11, w.wo0));
-            cell[640 + w.o1] = __fadd_rn(cell[640 + w.o1], __fmul_rn(w.a11, w.wo1));
+            cell[40 * DESC_NC + w.o0] = __fadd_rn(cell[40 * DESC_NC + w.o0], __fmul_rn(w.a11, w.wo0));
+            cell[40 * DESC_NC + w.o1] = __fadd_rn(cell[40 * DESC_NC + w.o1], __fmul_rn(w.a11, w.wo1));
           }
         };
         // Processes queue entries [0, m), m <= 96, three per lane with their loads overlapped.
@@ -388,14 +389,14 @@ namespace sb {
           const Sample b = fetch(queue[lane + 32], on1);
           const Sample c = fetch(queue[lane + 64], on2);
           const Weights wa = weights(a), wb = weights(b), wc = weights(c);
-          update(wa, on0 && lo_half);
-          update(wb, on1 && lo_half);
-          update(wc, on2 && lo_half);
-          __syncwarp();
-          update(wa, on0 && !lo_half);
-          update(wb, on1 && !lo_half);
-          update(wc, on2 && !lo_half);
-          __syncwarp();
+#pragma unroll
+          for (int ph = 0; ph < 32 / DESC_NC; ++ph)
+          {
+            update(wa, on0 && lphase == ph);
+            update(wb, on1 && lphase == ph);
+            update(wc, on2 && lphase == ph);
+            __syncwarp();
+          }
         };
 
         const int side = 2 * rounded_r + 1;
@@ -449,11 +450,11 @@ namespace sb {
 #pragma unroll
         for (int q = 0; q < 4; ++q)
         {
-          const float* pb = priv + (q * 32 + lane) * 16;
+          const float* pb = priv + (q * 32 + lane) * DESC_NC;
           float sum = 0.f;
-#pragma unroll 8
-          for (int j = 0; j < 16; ++j)
-            sum = __fadd_rn(sum, pb[(j + lane) & 15]);
+#pragma unroll
+          for (int j = 0; j < DESC_NC; ++j)
+            sum = __fadd_rn(sum, pb[(j + lane) & (DESC_NC - 1)]);
           hv[q] = sum;
         }
         __syncwarp();
@@ -517,7 +518,7 @@ namespace sb {
   int launch_descriptors(const PyramidDesc& P, const Keypoint* kp_oct, Keypoint* kp_out, float* desc,
                          int cap_kp, Counters* counters, cudaStream_t st)
   {
-    const int smem = DESC_WARPS * (128 * 16 + 128) * sizeof(float);
+    const int smem = DESC_WARPS * (128 * DESC_NC + 128) * sizeof(float);
     cudaFuncSetAttribute(descriptor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     descriptor_kernel<<<148 * 6, DESC_WARPS * 32, smem, st>>>(P, kp_oct, counters, cap_kp, kp_out, desc);
     return 1;
