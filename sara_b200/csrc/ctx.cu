@@ -28,6 +28,11 @@ namespace {
   struct Slot
   {
     cudaStream_t own_stream = nullptr;
+    // Octaves overlap: octave o + 1 only needs scale `downscale_index` of octave o, so the octaves
+    // run on alternating side streams chained by events and are joined back at the end.
+    cudaStream_t side[3] = {};
+    cudaEvent_t ev_down[kMaxOctaves] = {};
+    cudaEvent_t ev_join[3] = {};
     cudaStream_t stream = nullptr;  // stream of the frame in flight
     // pyramid arena (grown on demand)
     char* arena = nullptr;
@@ -390,10 +395,20 @@ namespace {
       bool staged = (mode == SARA_B200_PYRAMID_AUTO || mode == SARA_B200_PYRAMID_STAGE) && P.n_scales > 1;
       for (int s = 1; s < P.n_scales && staged; ++s)
         staged = stage_kernel_supported(S.stage_taps[s].n);
+      const cudaStream_t main_st = st;
+      bool side_used[3] = {false, false, false};
       for (int o = 0; o < P.n_octaves; ++o)
       {
         const OctaveDesc& oc = P.oct[o];
         const OctaveDesc* next = o + 1 < P.n_octaves ? &P.oct[o + 1] : nullptr;
+        if (staged && o > 0)
+        {
+          // Octave o starts as soon as its base exists (event recorded below, after the launch
+          // that wrote it) and runs beside the remaining scales of the octaves above it.
+          st = S.side[(o - 1) % 3];
+          side_used[(o - 1) % 3] = true;
+          CU(ctx, cudaStreamWaitEvent(st, S.ev_down[o - 1], 0));
+        }
         // The small octaves at the end of the pyramid run in one single-CTA launch.
         if (mode != SARA_B200_PYRAMID_GENERIC && o > 0 && oc.w * oc.h <= 4096)
         {
@@ -433,11 +448,17 @@ namespace {
                                next->h, next->pitch, st);
               ++S.pyramid_launches;
             }
+            if (next && s == S.downscale_index)
+              CU(ctx, cudaEventRecord(S.ev_down[o], st));  // the base of octave o + 1 is written
           }
-          if (next && !fuse_down && S.downscale_index == 0)
+          if (next && S.downscale_index == 0)
           {
-            launch_downscale(oc.G, oc.w, oc.h, oc.pitch, next->G, next->w, next->h, next->pitch, st);
-            ++S.pyramid_launches;
+            if (!fuse_down)
+            {
+              launch_downscale(oc.G, oc.w, oc.h, oc.pitch, next->G, next->w, next->h, next->pitch, st);
+              ++S.pyramid_launches;
+            }
+            CU(ctx, cudaEventRecord(S.ev_down[o], st));
           }
           continue;
         }
@@ -476,6 +497,14 @@ namespace {
           ++S.pyramid_launches;
         }
       }
+      // join the side streams back into the frame's stream
+      st = main_st;
+      for (int i = 0; i < 3; ++i)
+        if (side_used[i])
+        {
+          CU(ctx, cudaEventRecord(S.ev_join[i], S.side[i]));
+          CU(ctx, cudaStreamWaitEvent(st, S.ev_join[i], 0));
+        }
     }
     if (prof)
       CU(ctx, cudaEventRecord(S.ev[2], st));
@@ -657,6 +686,14 @@ int sara_b200_create(int device, const sara_b200_limits* limits, sara_b200_ctx**
   for (Slot& S : ctx->slots)
   {
     cudaError_t err = cudaStreamCreateWithFlags(&S.own_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 3 && err == cudaSuccess; ++i)
+    {
+      err = cudaStreamCreateWithFlags(&S.side[i], cudaStreamNonBlocking);
+      if (err == cudaSuccess)
+        err = cudaEventCreateWithFlags(&S.ev_join[i], cudaEventDisableTiming);
+    }
+    for (int i = 0; i < kMaxOctaves && err == cudaSuccess; ++i)
+      err = cudaEventCreateWithFlags(&S.ev_down[i], cudaEventDisableTiming);
     for (int i = 0; i < 9 && err == cudaSuccess; ++i)
       err = cudaEventCreate(&S.ev[i]);
     size_t bytes = 0;
@@ -737,6 +774,18 @@ void sara_b200_destroy(sara_b200_ctx* ctx)
     for (auto& ev : S.ev)
       if (ev)
         cudaEventDestroy(ev);
+    for (auto& e : S.ev_down)
+      if (e)
+        cudaEventDestroy(e);
+    for (auto& e : S.ev_join)
+      if (e)
+        cudaEventDestroy(e);
+    for (auto& sd : S.side)
+      if (sd)
+      {
+        cudaStreamSynchronize(sd);
+        cudaStreamDestroy(sd);
+      }
     if (S.own_stream)
       cudaStreamDestroy(S.own_stream);
   }
