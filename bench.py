@@ -38,7 +38,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 W4K, H4K = 3840, 2160
-FRAMES_PER_STEP = 4
+FRAMES_PER_STEP = int(os.environ.get("SARA_B200_BENCH_FRAMES", "4"))
 METRIC = "sift_keypoints_per_sec_4k"
 UNIT = "keypoints/s"
 ALGO_BYTES_PER_OCTAVE_PIXEL = 48  # 1 fp32 read + 6 Gaussian + 5 DoG fp32 writes

@@ -29,40 +29,28 @@ namespace sb {
     constexpr float kPi = 3.14159274101257324f;     // float(M_PI)
     constexpr float kTwoPi = 6.28318548202514648f;  // float(2. * M_PI)
 
-    // Polar gradient at (x, y) of layer f: (2 * |g|, atan2(gy, gx)) with the
-    // one-sided differences of the Gradient functor at the borders.
-    __device__ __forceinline__ void polar_gradient(const float* __restrict__ f, int w, int h, int pitch,
-                                                   int x, int y, float& mag, float& ori)
-    {
-      const float* row = f + static_cast<size_t>(y) * pitch;
-      const int xn = x == w - 1 ? x : x + 1;
-      const int xp = x == 0 ? x : x - 1;
-      const int yn = y == h - 1 ? y : y + 1;
-      const int yp = y == 0 ? y : y - 1;
-      const float gx = __fdiv_rn(__fsub_rn(__ldg(row + xn), __ldg(row + xp)), 2.f);
-      const float gy = __fdiv_rn(__fsub_rn(__ldg(f + static_cast<size_t>(yn) * pitch + x),
-                                           __ldg(f + static_cast<size_t>(yp) * pitch + x)),
-                                 2.f);
-      mag = __fmul_rn(2.f, __fsqrt_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy))));
-      ori = atan2f(gy, gx);
-    }
-
     constexpr int ORI_WARPS = 8;
 
     __global__ void __launch_bounds__(ORI_WARPS * 32)
         orientation_kernel(const __grid_constant__ PyramidDesc P, const Keypoint* __restrict__ ext,
-                           const Counters* __restrict__ counters, int cap_ext,
+                           Counters* __restrict__ counters, int cap_ext,
                            int* __restrict__ ori_count, float* __restrict__ oris)
     {
       __shared__ float s_priv[ORI_WARPS][36][32];
       __shared__ float s_hist[ORI_WARPS][2][36];
       const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
       const int n = min(counters->n_ext, cap_ext);
-      const int warps_per_grid = gridDim.x * ORI_WARPS;
       float(*priv)[32] = s_priv[wid];
 
-      for (int i = blockIdx.x * ORI_WARPS + wid; i < n; i += warps_per_grid)
+      // extrema are handed out through a device-side queue: their cost grows with the scale
+      while (true)
       {
+        int i = 0;
+        if (lane == 0)
+          i = atomicAdd(&counters->ori_next, 1);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= n)
+          break;
         const Keypoint kp = ext[i];
         const OctaveDesc& oc = P.oct[kp.o];
         const float* G = oc.G + static_cast<size_t>(kp.s) * oc.layer_stride;
@@ -82,20 +70,47 @@ namespace sb {
 
         const int side = 2 * radius + 1;
         const int count = side * side;
-        for (int t = lane; t < count; t += 32)
+        // three samples per lane and round, their gradient loads requested together
+        for (int t0 = lane; t0 < count; t0 += 96)
         {
-          const int v = t / side - radius;
-          const int u = t - (v + radius) * side - radius;
-          const int X = rx + u, Y = ry + v;
-          if (X < 0 || X >= w || Y < 0 || Y >= h)
-            continue;
-          float mag, ori;
-          polar_gradient(G, w, h, pitch, X, Y, mag, ori);
-          ori = ori < 0.f ? __fadd_rn(ori, kTwoPi) : ori;
-          int bin = static_cast<int>(floorf(__fmul_rn(__fdiv_rn(ori, kTwoPi), 36.f)));
-          bin %= 36;
-          const float weight = expf(__fdiv_rn(static_cast<float>(-(u * u + v * v)), denom));
-          priv[bin][lane] = __fadd_rn(priv[bin][lane], __fmul_rn(weight, mag));
+          float xn[3], xp[3], yn[3], yp[3];
+          int uu[3], vv[3];
+          bool on[3];
+#pragma unroll
+          for (int k = 0; k < 3; ++k)
+          {
+            const int t = t0 + 32 * k;
+            const int vr = t / side;
+            vv[k] = vr - radius;
+            uu[k] = t - vr * side - radius;
+            const int X = rx + uu[k], Y = ry + vv[k];
+            on[k] = t < count && X >= 0 && X < w && Y >= 0 && Y < h;
+            xn[k] = xp[k] = yn[k] = yp[k] = 0.f;
+            if (on[k])
+            {
+              // Gradient functor: central differences, one-sided at the borders (Differential.hpp:46-61)
+              const float* row = G + static_cast<size_t>(Y) * pitch;
+              xn[k] = __ldg(row + (X == w - 1 ? X : X + 1));
+              xp[k] = __ldg(row + (X == 0 ? X : X - 1));
+              yn[k] = __ldg(G + static_cast<size_t>(Y == h - 1 ? Y : Y + 1) * pitch + X);
+              yp[k] = __ldg(G + static_cast<size_t>(Y == 0 ? Y : Y - 1) * pitch + X);
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 3; ++k)
+          {
+            if (!on[k])
+              continue;
+            const float gx = __fdiv_rn(__fsub_rn(xn[k], xp[k]), 2.f);
+            const float gy = __fdiv_rn(__fsub_rn(yn[k], yp[k]), 2.f);
+            const float mag = __fmul_rn(2.f, __fsqrt_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy))));
+            float ori = atan2f(gy, gx);
+            ori = ori < 0.f ? __fadd_rn(ori, kTwoPi) : ori;
+            int bin = static_cast<int>(floorf(__fmul_rn(__fdiv_rn(ori, kTwoPi), 36.f)));
+            bin %= 36;
+            const float weight = expf(__fdiv_rn(static_cast<float>(-(uu[k] * uu[k] + vv[k] * vv[k])), denom));
+            priv[bin][lane] = __fadd_rn(priv[bin][lane], __fmul_rn(weight, mag));
+          }
         }
         __syncwarp();
 

@@ -25,26 +25,12 @@ namespace sb {
     }
 
     // ---- pass 1: classify every pixel of D(s, o), s = 1 .. n_scales - 3 ------
-    // LocalScaleSpaceExtremum + threshold + on_edge for one pixel whose value passed the
-    // threshold (RefineExtremum.cpp:407-437).  Returns the uint8 map value.
-    __device__ __forceinline__ uint8_t classify_pixel(const float* __restrict__ Dc, int layer_stride, int pitch, int x,
-                                                      int y, float v, float edge_ratio)
+    // Second half of LocalScaleSpaceExtremum + on_edge for a pixel that already is a
+    // non-strict extremum of its own layer and passed the threshold
+    // (RefineExtremum.cpp:407-437, Extrema.hpp:63-75).  Returns the uint8 map value.
+    __device__ __forceinline__ uint8_t classify_rest(const float* __restrict__ Dc, int layer_stride, int pitch, int x,
+                                                  int y, float v, bool is_max, bool is_min, float edge_ratio)
     {
-      // The 8 neighbours of the same layer decide for most pixels, so they go first and the
-      // two adjacent layers are only touched by pixels that are still candidates.
-      bool is_max = true, is_min = true;
-#pragma unroll
-      for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-        for (int dx = -1; dx <= 1; ++dx)
-          if (dx != 0 || dy != 0)
-          {
-            const float cc = ld(Dc, pitch, x + dx, y + dy);
-            is_max = is_max && (v >= cc);
-            is_min = is_min && (v <= cc);
-          }
-      if (!(is_max || is_min))
-        return 0;
       const float* Dp = Dc - layer_stride;
       const float* Dn = Dc + layer_stride;
 #pragma unroll
@@ -78,8 +64,11 @@ namespace sb {
     }
 
     // All octaves and scales in one launch.  A block is a tile of 128 x 32 pixels of one DoG
-    // layer: a thread takes 4 consecutive pixels (one float4 of centre values, one uchar4 of
-    // map), a warp is one raster row of the tile and adds its candidates to the row counter.
+    // layer; a thread owns 4 x 4 pixels.  It loads the 6 x 4 centre-layer values it needs as
+    // float4 rows, takes the two halo columns from its neighbour lanes by warp shuffle, and
+    // decides "non-strict extremum of its own 3 x 3" for its 16 pixels from registers with
+    // running max / min (v >= all 8 neighbours <=> v >= their max).  Only the few survivors
+    // that also pass the threshold touch the two adjacent layers.
     struct ClassifyTiles
     {
       int base[kMaxOctaves + 1];  // first tile of every octave
@@ -99,49 +88,113 @@ namespace sb {
       const int s = tile / per_layer + 1;
       tile -= (s - 1) * per_layer;
       const int ty = tile / T.tiles_x[o], tx = tile - ty * T.tiles_x[o];
-      const int x0 = (tx * 32 + threadIdx.x) * 4;
+      const int lane = threadIdx.x;
+      const int x0 = (tx * 32 + lane) * 4;
+      const int yb = ty * 32 + threadIdx.y * 4;  // first of the thread's 4 rows
       const int w = oct.w, h = oct.h, pitch = oct.pitch;
       const float thr = __fmul_rn(0.8f, ep.extremum_thres);
       const float* Dc = oct.D + static_cast<size_t>(s) * oct.layer_stride;
-      // four rows per thread: their centre values are requested together
-      float4 v4[4];
-      bool row_on[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
+
+      // Survivors of the in-layer test wait here; the whole block then finishes them together.
+      constexpr int LIST = 1024;
+      __shared__ int s_n;
+      __shared__ unsigned s_xy[LIST];     // x | y << 16
+      __shared__ float s_v[LIST];         // centre value, sign bit of the index word: polarity flags below
+      __shared__ unsigned char s_flag[LIST];  // bit 0: is_max, bit 1: is_min
+      if (threadIdx.x == 0 && threadIdx.y == 0)
+        s_n = 0;
+      __syncthreads();
+
+      if (yb < h)  // warp-uniform
       {
-        const int y = ty * 32 + threadIdx.y + 8 * k;
-        row_on[k] = x0 < w && ep.pad <= y && y < h - ep.pad;
-        v4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row_on[k])
-          v4[k] = __ldg(reinterpret_cast<const float4*>(Dc + static_cast<size_t>(y) * pitch + x0));
-      }
+        // R[r][c]: rows yb - 1 .. yb + 4 (clamped for the loads), columns x0 - 1 .. x0 + 4
+        float R[6][6];
+        const bool col_on = x0 < w;
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-      {
-        const int y = ty * 32 + threadIdx.y + 8 * k;
-        if (y >= h)
-          break;  // warp-uniform: a warp is one row
-        uchar4 types = make_uchar4(0, 0, 0, 0);
-        if (row_on[k])
+        for (int r = 0; r < 6; ++r)
         {
-          const float v[4] = {v4[k].x, v4[k].y, v4[k].z, v4[k].w};
-          uint8_t t[4] = {0, 0, 0, 0};
+          const int yy = min(max(yb - 1 + r, 0), h - 1);
+          const float* row = Dc + static_cast<size_t>(yy) * pitch;
+          float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (col_on)
+            v4 = __ldg(reinterpret_cast<const float4*>(row + x0));
+          R[r][1] = v4.x;
+          R[r][2] = v4.y;
+          R[r][3] = v4.z;
+          R[r][4] = v4.w;
+          float left = __shfl_up_sync(0xffffffffu, v4.w, 1);
+          float right = __shfl_down_sync(0xffffffffu, v4.x, 1);
+          if (lane == 0)
+            left = (col_on && x0 > 0) ? __ldg(row + x0 - 1) : 0.f;
+          if (lane == 31)
+            right = (col_on && x0 + 4 < w) ? __ldg(row + x0 + 4) : 0.f;
+          R[r][0] = left;
+          R[r][5] = right;
+        }
+
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+        {
+          const int y = yb + k;
+          if (y >= h)
+            break;  // warp-uniform
+          // the map row starts empty; survivors are filled in below
+          if (x0 < oct.map_pitch)
+            *reinterpret_cast<uchar4*>(oct.map + (static_cast<size_t>(s - 1) * h + y) * oct.map_pitch + x0) =
+                make_uchar4(0, 0, 0, 0);
+          // column-wise max / min over rows y - 1, y, y + 1
+          float cmx[6], cmn[6];
+#pragma unroll
+          for (int c = 0; c < 6; ++c)
+          {
+            cmx[c] = fmaxf(fmaxf(R[k][c], R[k + 1][c]), R[k + 2][c]);
+            cmn[c] = fminf(fminf(R[k][c], R[k + 1][c]), R[k + 2][c]);
+          }
+          const bool row_ok = col_on && ep.pad <= y && y < h - ep.pad;
 #pragma unroll
           for (int e = 0; e < 4; ++e)
           {
-            const int x = x0 + e;
-            // all the rejections are ANDed in the reference; the cheap threshold test goes first
-            if (ep.pad <= x && x < w - ep.pad && !(fabsf(v[e]) < thr))
-              t[e] = classify_pixel(Dc, oct.layer_stride, pitch, x, y, v[e], ep.edge_ratio);
+            const int c = e + 1, x = x0 + e;
+            const float v = R[k + 1][c];
+            const float nmax = fmaxf(fmaxf(cmx[c - 1], cmx[c + 1]), fmaxf(R[k][c], R[k + 2][c]));
+            const float nmin = fminf(fminf(cmn[c - 1], cmn[c + 1]), fminf(R[k][c], R[k + 2][c]));
+            const bool is_max = v >= nmax, is_min = v <= nmin;
+            // all the rejections are ANDed in the reference; the cheap ones go first
+            if (row_ok && ep.pad <= x && x < w - ep.pad && (is_max || is_min) && !(fabsf(v) < thr))
+            {
+              const int slot = atomicAdd(&s_n, 1);
+              if (slot < LIST)
+              {
+                s_xy[slot] = static_cast<unsigned>(x) | (static_cast<unsigned>(y) << 16);
+                s_v[slot] = v;
+                s_flag[slot] = static_cast<unsigned char>((is_max ? 1 : 0) | (is_min ? 2 : 0));
+              }
+              else
+              {
+                // list full (never seen on natural images): finish this one on the spot
+                const uint8_t t = classify_rest(Dc, oct.layer_stride, pitch, x, y, v, is_max, is_min, ep.edge_ratio);
+                if (t != 0)
+                {
+                  oct.map[(static_cast<size_t>(s - 1) * h + y) * oct.map_pitch + x] = t;
+                  atomicAdd(oct.row_count + (s - 1) * h + y, 1);
+                }
+              }
+            }
           }
-          types = make_uchar4(t[0], t[1], t[2], t[3]);
         }
-        if (x0 < oct.map_pitch)
-          *reinterpret_cast<uchar4*>(oct.map + (static_cast<size_t>(s - 1) * h + y) * oct.map_pitch + x0) = types;
-        const int mine = (types.x != 0) + (types.y != 0) + (types.z != 0) + (types.w != 0);
-        const int total = __reduce_add_sync(0xffffffffu, mine);
-        if (threadIdx.x == 0 && total != 0)
-          atomicAdd(oct.row_count + (s - 1) * h + y, total);
+      }
+      __syncthreads();
+      const int n_list = min(s_n, LIST);
+      for (int i = threadIdx.y * 32 + threadIdx.x; i < n_list; i += 256)
+      {
+        const int x = static_cast<int>(s_xy[i] & 0xffffu), y = static_cast<int>(s_xy[i] >> 16);
+        const uint8_t t = classify_rest(Dc, oct.layer_stride, pitch, x, y, s_v[i], (s_flag[i] & 1) != 0,
+                                        (s_flag[i] & 2) != 0, ep.edge_ratio);
+        if (t != 0)
+        {
+          oct.map[(static_cast<size_t>(s - 1) * h + y) * oct.map_pitch + x] = t;
+          atomicAdd(oct.row_count + (s - 1) * h + y, 1);
+        }
       }
     }
 
