@@ -69,6 +69,8 @@ namespace sb {
     // decides "non-strict extremum of its own 3 x 3" for its 16 pixels from registers with
     // running max / min (v >= all 8 neighbours <=> v >= their max).  Only the few survivors
     // that also pass the threshold touch the two adjacent layers.
+    constexpr int CLS_RT = 4;  // rows per thread of classify_kernel (a block covers 128 x 8 * CLS_RT pixels)
+
     struct ClassifyTiles
     {
       int base[kMaxOctaves + 1];  // first tile of every octave
@@ -90,7 +92,7 @@ namespace sb {
       const int ty = tile / T.tiles_x[o], tx = tile - ty * T.tiles_x[o];
       const int lane = threadIdx.x;
       const int x0 = (tx * 32 + lane) * 4;
-      const int yb = ty * 32 + threadIdx.y * 4;  // first of the thread's 4 rows
+      const int yb = (ty * 8 + threadIdx.y) * CLS_RT;  // first of the thread's rows
       const int w = oct.w, h = oct.h, pitch = oct.pitch;
       const float thr = __fmul_rn(0.8f, ep.extremum_thres);
       const float* Dc = oct.D + static_cast<size_t>(s) * oct.layer_stride;
@@ -107,11 +109,11 @@ namespace sb {
 
       if (yb < h)  // warp-uniform
       {
-        // R[r][c]: rows yb - 1 .. yb + 4 (clamped for the loads), columns x0 - 1 .. x0 + 4
-        float R[6][6];
+        // R[r][c]: rows yb - 1 .. yb + CLS_RT (clamped for the loads), columns x0 - 1 .. x0 + 4
+        float R[CLS_RT + 2][6];
         const bool col_on = x0 < w;
 #pragma unroll
-        for (int r = 0; r < 6; ++r)
+        for (int r = 0; r < CLS_RT + 2; ++r)
         {
           const int yy = min(max(yb - 1 + r, 0), h - 1);
           const float* row = Dc + static_cast<size_t>(yy) * pitch;
@@ -133,7 +135,7 @@ namespace sb {
         }
 
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
+        for (int k = 0; k < CLS_RT; ++k)
         {
           const int y = yb + k;
           if (y >= h)
@@ -547,7 +549,7 @@ namespace sb {
     for (int o = 0; o < P.n_octaves; ++o)
     {
       T.tiles_x[o] = (P.oct[o].w + 127) / 128;
-      T.tiles_y[o] = (P.oct[o].h + 31) / 32;
+      T.tiles_y[o] = (P.oct[o].h + 8 * CLS_RT - 1) / (8 * CLS_RT);
       T.base[o + 1] = T.base[o] + T.tiles_x[o] * T.tiles_y[o] * n_s;
     }
     if (T.base[P.n_octaves] > 0)
