@@ -154,6 +154,9 @@ typedef enum sara_b200_pyramid_mode
   SARA_B200_PYRAMID_FUSED = 3    /* TMA-staged fused octave kernel, one launch per octave (default schedule) */
 } sara_b200_pyramid_mode;
 SARA_B200_API int sara_b200_set_pyramid_mode(sara_b200_ctx* ctx, int mode);
+/* Octave o + 1 only needs one scale of octave o, so by default the octaves of a frame overlap
+ * on side streams.  Turning this off serialises them (used to time single launches alone). */
+SARA_B200_API int sara_b200_set_octave_overlap(sara_b200_ctx* ctx, int on);
 
 /* Record CUDA events around the stages (sara_b200_last_timings). */
 SARA_B200_API int sara_b200_set_profiling(sara_b200_ctx* ctx, int on);

@@ -83,7 +83,7 @@ SYMBOLS = [
     "sara_b200_version", "sara_b200_last_error", "sara_b200_default_pyramid_params",
     "sara_b200_default_sift_args", "sara_b200_default_dog_args", "sara_b200_create",
     "sara_b200_destroy", "sara_b200_host_alloc", "sara_b200_host_free", "sara_b200_set_profiling",
-    "sara_b200_set_pyramid_mode",
+    "sara_b200_set_pyramid_mode", "sara_b200_set_octave_overlap",
     "sara_b200_last_timings", "sara_b200_sift", "sara_b200_sift_enqueue", "sara_b200_collect",
     "sara_b200_device_results", "sara_b200_wait", "sara_b200_dog_extrema",
     "sara_b200_pyramid_enqueue", "sara_b200_num_octaves", "sara_b200_num_scales",
@@ -121,6 +121,7 @@ def load_library() -> C.CDLL:
     L.sara_b200_host_free.restype = None
     L.sara_b200_set_profiling.argtypes = [vp, C.c_int]
     L.sara_b200_set_pyramid_mode.argtypes = [vp, C.c_int]
+    L.sara_b200_set_octave_overlap.argtypes = [vp, C.c_int]
     L.sara_b200_last_timings.argtypes = [vp, C.c_int, C.POINTER(Timings)]
     L.sara_b200_sift.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(_SiftArgs), vp, vp, C.c_int, ip]
     L.sara_b200_sift_enqueue.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.POINTER(_SiftArgs), vp]
@@ -251,6 +252,9 @@ class SiftContext:
         """0 auto, 1 generic, 2 per-stage marching kernel, 3 fused octave kernel (same bits)."""
         mode = {"auto": 0, "generic": 1, "stage": 2, "fused": 3}.get(mode, mode)
         self._check(self._L.sara_b200_set_pyramid_mode(self._ctx, int(mode)))
+
+    def set_octave_overlap(self, on: bool):
+        self._check(self._L.sara_b200_set_octave_overlap(self._ctx, int(on)))
 
     def set_profiling(self, on: bool):
         self._check(self._L.sara_b200_set_profiling(self._ctx, int(on)))

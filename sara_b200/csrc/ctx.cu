@@ -76,6 +76,7 @@ struct sara_b200_ctx
   int cap_kp = 0, cap_ext = 0, cap_cand = 0;
   bool profiling = false;
   int pyramid_mode = SARA_B200_PYRAMID_AUTO;
+  bool octave_overlap = true;
   std::vector<Slot> slots;
   char err[512] = "";
 };
@@ -401,7 +402,7 @@ namespace {
       {
         const OctaveDesc& oc = P.oct[o];
         const OctaveDesc* next = o + 1 < P.n_octaves ? &P.oct[o + 1] : nullptr;
-        if (staged && o > 0)
+        if (staged && o > 0 && ctx->octave_overlap)
         {
           // Octave o starts as soon as its base exists (event recorded below, after the launch
           // that wrote it) and runs beside the remaining scales of the octaves above it.
@@ -824,6 +825,14 @@ int sara_b200_set_pyramid_mode(sara_b200_ctx* ctx, int mode)
   if (mode < SARA_B200_PYRAMID_AUTO || mode > SARA_B200_PYRAMID_FUSED)
     return fail(ctx, SARA_B200_ERR_BAD_ARG, "unknown pyramid mode %d", mode);
   ctx->pyramid_mode = mode;
+  return 0;
+}
+
+int sara_b200_set_octave_overlap(sara_b200_ctx* ctx, int on)
+{
+  if (!ctx)
+    return SARA_B200_ERR_BAD_ARG;
+  ctx->octave_overlap = on != 0;
   return 0;
 }
 
