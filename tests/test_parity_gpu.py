@@ -219,3 +219,41 @@ def test_capacity_overflow_is_reported():
         c.compute_sift_keypoints(S.tex(640, 480, 3), sb.ImagePyramidParams(first_octave_index=0))
     assert ei.value.code == -5
     c.close()
+
+
+# ---- full SIFT on other parameter sets (generic kernels, other thresholds) -------------
+@pytest.mark.parametrize("kw,args", [
+    (dict(scale_count_per_octave=5, scale_geometric_factor=float(np.float32(2.0) ** np.float32(0.5))), {}),
+    (dict(scale_count_per_octave=7, scale_geometric_factor=float(np.float32(2.0) ** np.float32(0.25))), {}),
+    (dict(num_octaves_max=3), dict(extremum_thres=0.02, edge_ratio_thres=5.0)),
+    (dict(), dict(extremum_thres=0.003, extremum_refinement_iter=2)),
+])
+def test_sift_other_parameters(ctx, kw, args):
+    img = S.tex(512, 384, 91)
+    p_gpu, p_ref = _pp(0, **kw)
+    a = dict(gauss_truncate=4.0, extremum_thres=0.01, edge_ratio_thres=10.0, extremum_refinement_iter=5)
+    a.update(args)
+    ref = O.compute_sift_keypoints(img, p_ref, a["gauss_truncate"], a["extremum_thres"], a["edge_ratio_thres"],
+                                   a["extremum_refinement_iter"], parallel=True)
+    kl = ctx.compute_sift_keypoints(img, p_gpu, a["gauss_truncate"], a["extremum_thres"], a["edge_ratio_thres"],
+                                    a["extremum_refinement_iter"])
+    assert_pyramids_identical(ctx, ref)
+    assert_extrema_identical(ctx.extrema(), ref.extrema)
+    assert len(ref.keypoints) > 20
+    compare_keypoints(kl.features, kl.descriptors, ref.keypoints, ref.descriptors)
+
+
+@pytest.mark.parametrize("w,h", [(2000, 40), (40, 1500), (641, 479), (1023, 767)])
+def test_sift_ragged_shapes(ctx, w, h):
+    c = sb.SiftContext(max(w, 64), max(h, 64), max_keypoints=65536)
+    try:
+        img = S.tex(w, h, 17)
+        p_gpu, p_ref = _pp(0)
+        ref = O.compute_sift_keypoints(img, p_ref, parallel=True)
+        kl = c.compute_sift_keypoints(img, p_gpu)
+        assert_pyramids_identical(c, ref)
+        assert_extrema_identical(c.extrema(), ref.extrema)
+        if len(ref.keypoints):
+            compare_keypoints(kl.features, kl.descriptors, ref.keypoints, ref.descriptors)
+    finally:
+        c.close()

@@ -114,3 +114,29 @@ def test_extrema_order_and_determinism_at_4k(ctx4k):
     # truncation of SIFT.hpp:204-238 (quirk N6) gives negative trilinear weights.
     assert np.isfinite(a.descriptors).all() and a.descriptors.max() <= 255
     assert len(a) > 5000
+
+
+def test_8k_frame_pyramid_implementations_agree():
+    """Largest configuration the reference benchmarks (7680x4320): grid sizes,
+    arena offsets and 32-bit index arithmetic at 33 M pixels per layer."""
+    c = sb.SiftContext(7680, 4320, max_keypoints=262144)
+    try:
+        rng = np.random.default_rng(11)
+        img = rng.random((4320, 7680), dtype=np.float32)
+        pp = sb.ImagePyramidParams(first_octave_index=0)
+        ref = None
+        for mode in ("generic", "stage"):
+            c.set_pyramid_mode(mode)
+            c.pyramid_enqueue(0, img, pp)
+            c.wait(0)
+            got = [c.dog_layer(s, o).copy() for o in (0, 1, c.num_octaves() - 1) for s in (0, 4)] + \
+                  [c.gaussian_layer(5, 0).copy()]
+            if ref is None:
+                ref = got
+            else:
+                for a, b in zip(ref, got):
+                    assert a.tobytes() == b.tobytes()
+        kl = c.compute_sift_keypoints(img[:, :], pp)
+        assert c.num_octaves() == 11 and len(kl) >= 0
+    finally:
+        c.close()
