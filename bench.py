@@ -182,6 +182,13 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    try:  # keep this rank's host thread and its pinned buffers on the CPUs next to its GPU
+        import pynvml as nv
+
+        nv.nvmlInit()
+        nv.nvmlDeviceSetCpuAffinity(nv.nvmlDeviceGetHandleByIndex(local_rank))
+    except Exception:
+        pass
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -348,7 +355,8 @@ def run_ours(args):
                        "frames_per_step_per_gpu": F, "keypoints_per_step": tot_kp // args.steps,
                        "l2": f"inputs larger than L2: {F} distinct 33 MB frames per step, 531 MB of pyramid written per frame",
                        "parallelism": f"frames sharded {F}/GPU/step, no data-path collective"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": F * W4K * H4K * 4, "d2h_bytes_per_step": d2h[0],
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * F * W4K * H4K * 4,
+                    "d2h_bytes_per_step": world * d2h[0],
                     "ms_per_step": 1e3 * max_e2e / args.steps},
             "gpu_launches": int(launches_per_frame) * F * args.steps,
             "clocks": clocks, "roofline": roofline, "stage_ms_per_frame": stage_ms, "cpu_baseline": cpu_baseline,
