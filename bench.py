@@ -334,8 +334,10 @@ def run_ours(args):
                                 "bytes_per_octave_pixel": ALGO_BYTES_PER_OCTAVE_PIXEL}}
         stage_ms = {k: float(np.mean(v)) for k, v in stage_acc.items()}
 
-        # ---- CPU baseline on this box's host cores (bounded sample) -------------------------
+        # ---- CPU baseline on this box's host cores (bounded sample; reported at N = 1 only) --
         try:
+            if world > 1:
+                raise RuntimeError("reported at N = 1 only")
             n_cpu, secs_cpu, cores = cpu_oracle_run(frames, 2, 1, mode=1)
             cpu_baseline = {"value": n_cpu / secs_cpu, "unit": UNIT, "cores": cores, "kind": "port",
                             "sample": "2 of the benchmark's 3840x2160 frames after 1 warm-up, every stage OpenMP over all host threads",
