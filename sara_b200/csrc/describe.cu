@@ -333,11 +333,13 @@ namespace sb {
           }
           return sm;
         };
+        // What one kept sample adds to the histogram: 8 (address, value) pairs.  A missing
+        // +1 neighbour (xi == 3 or yi == 3) aliases the cell itself with a zero value, so the
+        // update is branch-free (x + 0 == x).
         struct Weights
         {
-          int cell, o0, o1;
-          float a00, a01, a10, a11, wo0, wo1;
-          bool x1, y1;
+          int p0, p1, dx, dy;  // float offsets into the lane's histogram copy
+          float v[8];
         };
         auto weights = [&](const Sample& sm) {
           Weights w;
@@ -361,41 +363,39 @@ namespace sb {
           // (xi, yi) in [0, 3]; the +1 neighbours exist for xi, yi < 3
           const float wy0 = __fsub_rn(1.f, yfrac), wx0 = __fsub_rn(1.f, xfrac);
           const bool x1 = xi < 3, y1 = yi < 3;
-          w.cell = ((4 * yi + xi) * 8) * DESC_NC + lcopy;
-          w.o0 = (oi & 7) * DESC_NC;
-          w.o1 = ((oi + 1) & 7) * DESC_NC;
-          w.a00 = __fmul_rn(wy0, wx0);
-          w.a01 = x1 ? __fmul_rn(wy0, xfrac) : 0.f;
-          w.a10 = y1 ? __fmul_rn(yfrac, wx0) : 0.f;
-          w.a11 = (x1 && y1) ? __fmul_rn(yfrac, xfrac) : 0.f;
-          w.x1 = x1;
-          w.y1 = y1;
-          w.wo0 = wo0;
-          w.wo1 = wo1;
+          const int cell = ((4 * yi + xi) * 8) * DESC_NC + lcopy;
+          w.p0 = cell + (oi & 7) * DESC_NC;
+          w.p1 = cell + ((oi + 1) & 7) * DESC_NC;
+          w.dx = x1 ? 8 * DESC_NC : 0;
+          w.dy = y1 ? 32 * DESC_NC : 0;
+          const float a00 = __fmul_rn(wy0, wx0);
+          const float a01 = x1 ? __fmul_rn(wy0, xfrac) : 0.f;
+          const float a10 = y1 ? __fmul_rn(yfrac, wx0) : 0.f;
+          const float a11 = (x1 && y1) ? __fmul_rn(yfrac, xfrac) : 0.f;
+          w.v[0] = __fmul_rn(a00, wo0);
+          w.v[1] = __fmul_rn(a00, wo1);
+          w.v[2] = __fmul_rn(a01, wo0);
+          w.v[3] = __fmul_rn(a01, wo1);
+          w.v[4] = __fmul_rn(a10, wo0);
+          w.v[5] = __fmul_rn(a10, wo1);
+          w.v[6] = __fmul_rn(a11, wo0);
+          w.v[7] = __fmul_rn(a11, wo1);
           return w;
         };
-        // the 8 bin updates of one sample for the lanes of one half-warp
+        // the 8 bin updates of one sample, for the lanes whose turn it is
         auto update = [&](const Weights& w, bool mine) {
           if (!mine)
             return;
-          float* cell = priv + w.cell;
-          cell[w.o0] = __fadd_rn(cell[w.o0], __fmul_rn(w.a00, w.wo0));
-          cell[w.o1] = __fadd_rn(cell[w.o1], __fmul_rn(w.a00, w.wo1));
-          if (w.x1)
-          {
-            cell[8 * DESC_NC + w.o0] = __fadd_rn(cell[8 * DESC_NC + w.o0], __fmul_rn(w.a01, w.wo0));
-            cell[8 * DESC_NC + w.o1] = __fadd_rn(cell[8 * DESC_NC + w.o1], __fmul_rn(w.a01, w.wo1));
-          }
-          if (w.y1)
-          {
-            cell[32 * DESC_NC + w.o0] = __fadd_rn(cell[32 * DESC_NC + w.o0], __fmul_rn(w.a10, w.wo0));
-            cell[32 * DESC_NC + w.o1] = __fadd_rn(cell[32 * DESC_NC + w.o1], __fmul_rn(w.a10, w.wo1));
-          }
-          if (w.x1 && w.y1)
-          {
-            cell[40 * DESC_NC + w.o0] = __fadd_rn(cell[40 * DESC_NC + w.o0], __fmul_rn(w.a11, w.wo0));
-            cell[40 * DESC_NC + w.o1] = __fadd_rn(cell[40 * DESC_NC + w.o1], __fmul_rn(w.a11, w.wo1));
-          }
+          float* q0 = priv + w.p0;
+          float* q1 = priv + w.p1;
+          q0[0] = __fadd_rn(q0[0], w.v[0]);
+          q1[0] = __fadd_rn(q1[0], w.v[1]);
+          q0[w.dx] = __fadd_rn(q0[w.dx], w.v[2]);
+          q1[w.dx] = __fadd_rn(q1[w.dx], w.v[3]);
+          q0[w.dy] = __fadd_rn(q0[w.dy], w.v[4]);
+          q1[w.dy] = __fadd_rn(q1[w.dy], w.v[5]);
+          q0[w.dx + w.dy] = __fadd_rn(q0[w.dx + w.dy], w.v[6]);
+          q1[w.dx + w.dy] = __fadd_rn(q1[w.dx + w.dy], w.v[7]);
         };
         // Processes queue entries [0, m), m <= 96, three per lane with their loads overlapped.
         auto drain = [&](int m) {
