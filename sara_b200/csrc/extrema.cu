@@ -77,7 +77,7 @@ namespace sb {
       int tiles_x[kMaxOctaves], tiles_y[kMaxOctaves];
     };
 
-    __global__ void __launch_bounds__(256)
+    __global__ void __launch_bounds__(256, 4)
         classify_kernel(const __grid_constant__ PyramidDesc P, const __grid_constant__ ClassifyTiles T,
                         const ExtremaParams ep)
     {
