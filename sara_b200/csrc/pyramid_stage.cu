@@ -219,35 +219,67 @@ namespace sb {
           }
           if (x_ok && yb + 3 >= y0 && yb < y1)
           {
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
+            // G(s-1) at (x, y) is still in the staging ring (blocks t - 1 and t): rel = y - Y
+            const int rel0 = yb - Y;
+            float* po = prm.out + static_cast<size_t>(yb) * prm.pitch + x;
+            float* pd = prm.dog != nullptr ? prm.dog + static_cast<size_t>(yb) * prm.pitch + x : nullptr;
+            if (pair_ok && yb >= y0 && yb + 3 < y1)
             {
-              const int y = yb + r;
-              if (y < y0 || y >= y1)
-                continue;
-              const size_t o = static_cast<size_t>(y) * prm.pitch + x;
-              const float g0 = lo2(acc[r]), g1 = hi2(acc[r]);
-              // G(s-1) at (x, y) is still in the staging ring (blocks t - 1 and t)
-              const int rel = y - Y;
-              const float2 pv =
-                  *reinterpret_cast<const float2*>(raw + ((rel >> 4) & 3) * (R * BW) + (rel & 15) * BW + S::LEAD + c_i);
-              if (pair_ok)
+              // common case: four full rows, two columns each
+#pragma unroll
+              for (int r = 0; r < 4; ++r)
               {
-                *reinterpret_cast<float2*>(prm.out + o) = make_float2(g0, g1);
-                if (prm.dog != nullptr)
-                  *reinterpret_cast<float2*>(prm.dog + o) = make_float2(__fsub_rn(g0, pv.x), __fsub_rn(g1, pv.y));
+                const int rel = rel0 + r;
+                const float2 pv = *reinterpret_cast<const float2*>(raw + ((rel >> 4) & 3) * (R * BW) + (rel & 15) * BW +
+                                                                   S::LEAD + c_i);
+                const float g0 = lo2(acc[r]), g1 = hi2(acc[r]);
+                *reinterpret_cast<float2*>(po + static_cast<size_t>(r) * prm.pitch) = make_float2(g0, g1);
+                if (pd != nullptr)
+                  *reinterpret_cast<float2*>(pd + static_cast<size_t>(r) * prm.pitch) =
+                      make_float2(__fsub_rn(g0, pv.x), __fsub_rn(g1, pv.y));
               }
-              else
+              if (prm.nextG != nullptr)
               {
-                prm.out[o] = g0;
-                if (prm.dog != nullptr)
-                  prm.dog[o] = __fsub_rn(g0, pv.x);
+                // downscale(G(s), 2): even rows and columns (x is even)
+                const int xx = x >> 1;
+                if (xx < prm.nw)
+#pragma unroll
+                  for (int r = 0; r < 4; ++r)
+                    if (((yb + r) & 1) == 0 && ((yb + r) >> 1) < prm.nh)
+                      prm.nextG[static_cast<size_t>((yb + r) >> 1) * prm.npitch + xx] = lo2(acc[r]);
               }
-              if (prm.nextG != nullptr && (y & 1) == 0)
+            }
+            else
+            {
+#pragma unroll
+              for (int r = 0; r < 4; ++r)
               {
-                const int xx = x >> 1, yy = y >> 1;
-                if (xx < prm.nw && yy < prm.nh)
-                  prm.nextG[static_cast<size_t>(yy) * prm.npitch + xx] = g0;
+                const int y = yb + r;
+                if (y < y0 || y >= y1)
+                  continue;
+                const size_t o = static_cast<size_t>(r) * prm.pitch;
+                const float g0 = lo2(acc[r]), g1 = hi2(acc[r]);
+                const int rel = rel0 + r;
+                const float2 pv = *reinterpret_cast<const float2*>(raw + ((rel >> 4) & 3) * (R * BW) + (rel & 15) * BW +
+                                                                   S::LEAD + c_i);
+                if (pair_ok)
+                {
+                  *reinterpret_cast<float2*>(po + o) = make_float2(g0, g1);
+                  if (pd != nullptr)
+                    *reinterpret_cast<float2*>(pd + o) = make_float2(__fsub_rn(g0, pv.x), __fsub_rn(g1, pv.y));
+                }
+                else
+                {
+                  po[o] = g0;
+                  if (pd != nullptr)
+                    pd[o] = __fsub_rn(g0, pv.x);
+                }
+                if (prm.nextG != nullptr && (y & 1) == 0)
+                {
+                  const int xx = x >> 1, yy = y >> 1;
+                  if (xx < prm.nw && yy < prm.nh)
+                    prm.nextG[static_cast<size_t>(yy) * prm.npitch + xx] = g0;
+                }
               }
             }
           }
