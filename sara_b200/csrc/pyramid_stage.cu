@@ -205,9 +205,20 @@ namespace sb {
           const float* col = ring + c_i;
           const int* tab = rowtab + 4 * c_q;
           u64 win[K + 3];
+          // ring-row offsets: 16-byte broadcast loads (tab is 16-byte aligned: 4 * c_q entries in)
+          int toff[(K + 3 + 3) & ~3];
+#pragma unroll
+          for (int n4 = 0; n4 < (K + 3 + 3) / 4; ++n4)
+          {
+            const int4 tv = *reinterpret_cast<const int4*>(tab + 4 * n4);
+            toff[4 * n4] = tv.x;
+            toff[4 * n4 + 1] = tv.y;
+            toff[4 * n4 + 2] = tv.z;
+            toff[4 * n4 + 3] = tv.w;
+          }
 #pragma unroll
           for (int n = 0; n < K + 3; ++n)
-            win[n] = *reinterpret_cast<const u64*>(col + tab[n]);
+            win[n] = *reinterpret_cast<const u64*>(col + toff[n]);
           u64 acc[4] = {0ull, 0ull, 0ull, 0ull};
 #pragma unroll
           for (int j = 0; j < K; ++j)
