@@ -103,8 +103,10 @@ namespace sb {
     int pad;
     int refine_iter;
   };
+  int launch_classify(const PyramidDesc& P, const ExtremaParams& ep, int n_segments, int o_lo, int o_hi,
+                      bool zero_counts, cudaStream_t st);
   int launch_extrema(const PyramidDesc& P, const ExtremaParams& ep, int n_segments, int* seg_offsets,
-                     Candidate* cand, int cap_cand, Keypoint* ext_tmp, uint8_t* keep, int* bsums,
+                     Candidate* cand, int cap_cand, Keypoint* ext_tmp, int classified_upto, int* bsums,
                      Keypoint* ext, int cap_ext, Counters* counters, cudaStream_t st);
   int launch_orientation(const PyramidDesc& P, const Keypoint* ext, int cap_ext, int* ori_count,
                          float* oris, int* bsums, Keypoint* kp_oct, int cap_kp, Counters* counters,

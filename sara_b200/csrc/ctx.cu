@@ -61,10 +61,11 @@ namespace {
     std::vector<Taps> stage_taps;  // per scale s >= 1
     bool busy = false;
     bool has_keypoints = false;  // the last frame ran the keypoint stages
+    int classified_upto = 0;     // octaves already classified while the pyramid was still running
     cudaEvent_t ev[9] = {};  // [7], [8]: around the pyramid's longest launch
     double top_kernel_bytes = 0.;
     sara_b200_timings timings{};
-    int pyramid_launches = 0, total_launches = 0;
+    int pyramid_launches = 0, total_launches = 0, extra_launches = 0;
   };
 
   }  // namespace
@@ -322,8 +323,11 @@ namespace {
   }
 
   // Gaussian pyramid + DoG pyramid of one frame.
+  // `early`: extrema parameters when the caller goes on to the extrema stage; octave 0 is then
+  // classified as soon as its own DoG layers exist, beside the smaller octaves still being built.
   int enqueue_pyramid(sara_b200_ctx* ctx, Slot& S, const float* image, int w, int h, bool on_device,
-                      const sara_b200_pyramid_params& pp, float gauss_truncate, cudaStream_t st)
+                      const sara_b200_pyramid_params& pp, float gauss_truncate, cudaStream_t st,
+                      const ExtremaParams* early = nullptr)
   {
     Geometry g;
     int rc = plan_geometry(ctx, w, h, pp, &g);
@@ -334,6 +338,8 @@ namespace {
       return rc;
     S.stream = st;
     S.pyramid_launches = 0;
+    S.extra_launches = 0;
+    S.classified_upto = 0;
     S.top_kernel_bytes = 0.;
     const bool prof = ctx->profiling;
     if (prof)
@@ -461,6 +467,13 @@ namespace {
             }
             CU(ctx, cudaEventRecord(S.ev_down[o], st));
           }
+          if (o == 0 && early != nullptr && ctx->octave_overlap && P.n_octaves > 1 && P.n_scales >= 4 &&
+              S.n_segments > 0)
+          {
+            // octave 0 is complete on this stream: classify it now (its DoG layers are still in L2)
+            S.extra_launches = launch_classify(P, *early, S.n_segments, 0, 1, true, st);
+            S.classified_upto = 1;
+          }
           continue;
         }
         if (fused)
@@ -510,7 +523,7 @@ namespace {
     if (prof)
       CU(ctx, cudaEventRecord(S.ev[2], st));
     CU(ctx, cudaGetLastError());
-    S.total_launches = S.pyramid_launches;
+    S.total_launches = S.pyramid_launches + S.extra_launches;
     return 0;
   }
 
@@ -529,7 +542,7 @@ namespace {
     {
       ExtremaParams ep{extremum_thres, edge_ratio, pad, refine_iter};
       S.total_launches += launch_extrema(S.P, ep, S.n_segments, S.seg_offsets, S.cand, ctx->cap_cand,
-                                         S.ext_tmp, nullptr, S.scratch, S.ext, ctx->cap_ext, S.counters, st);
+                                         S.ext_tmp, S.classified_upto, S.scratch, S.ext, ctx->cap_ext, S.counters, st);
     }
     if (ctx->profiling)
       CU(ctx, cudaEventRecord(S.ev[3], st));
@@ -864,8 +877,12 @@ int sara_b200_sift_enqueue(sara_b200_ctx* ctx, int slot, const float* image, int
                 "minimum!");
   CU(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : S.own_stream;
+  if (args->extremum_refinement_iter < 1)  // it becomes img_padding_sz (quirk N1); checked before any launch
+    return fail(ctx, SARA_B200_ERR_BAD_ARG,
+                "img_padding_sz must be >= 1 (the 3x3x3 neighbourhood must stay inside the layer)");
+  const ExtremaParams early{args->extremum_thres, args->edge_ratio_thres, args->extremum_refinement_iter, 5};
   rc = enqueue_pyramid(ctx, S, image, w, h, image_on_device != 0, args->pyramid_params,
-                       args->gauss_truncate, st);
+                       args->gauss_truncate, st, &early);
   if (rc)
     return rc;
   // Quirk N1 (SIFT.cpp:45-51 vs DoG.hpp:72-78): extremum_refinement_iter lands in
@@ -972,8 +989,13 @@ int sara_b200_dog_extrema(sara_b200_ctx* ctx, int slot, const float* image, int 
                 "minimum!");
   CU(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = S.own_stream;
+  if (args->img_padding_sz < 1)
+    return fail(ctx, SARA_B200_ERR_BAD_ARG,
+                "img_padding_sz must be >= 1 (the 3x3x3 neighbourhood must stay inside the layer)");
+  const ExtremaParams early{args->extremum_thres, args->edge_ratio_thres, args->img_padding_sz,
+                            args->extremum_refinement_iter};
   rc = enqueue_pyramid(ctx, S, image, w, h, image_on_device != 0, args->pyramid_params,
-                       args->gauss_truncate, st);
+                       args->gauss_truncate, st, &early);
   if (rc)
     return rc;
   rc = enqueue_extrema(ctx, S, args->extremum_thres, args->edge_ratio_thres, args->img_padding_sz,

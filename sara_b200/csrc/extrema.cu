@@ -536,27 +536,35 @@ namespace sb {
 
   }  // namespace
 
-  int launch_extrema(const PyramidDesc& P, const ExtremaParams& ep, int n_segments, int* seg_offsets,
-                     Candidate* cand, int cap_cand, Keypoint* ext_tmp, uint8_t* keep_unused, int* scratch,
-                     Keypoint* ext, int cap_ext, Counters* counters, cudaStream_t st)
+  // Classifies octaves [o_lo, o_hi).  The row counters of ALL octaves are zeroed when
+  // `zero_counts` is set (they are contiguous, starting at octave 0's).
+  int launch_classify(const PyramidDesc& P, const ExtremaParams& ep, int n_segments, int o_lo, int o_hi,
+                      bool zero_counts, cudaStream_t st)
   {
-    (void) keep_unused;
-    int launches = 0;
     const int n_s = P.n_scales - 3;
-    // row counts of all octaves are contiguous, starting at octave 0's.
-    cudaMemsetAsync(P.oct[0].row_count, 0, sizeof(int) * n_segments, st);
+    if (zero_counts)
+      cudaMemsetAsync(P.oct[0].row_count, 0, sizeof(int) * n_segments, st);
     ClassifyTiles T{};
     for (int o = 0; o < P.n_octaves; ++o)
     {
+      const bool in = o >= o_lo && o < o_hi;
       T.tiles_x[o] = (P.oct[o].w + 127) / 128;
       T.tiles_y[o] = (P.oct[o].h + 8 * CLS_RT - 1) / (8 * CLS_RT);
-      T.base[o + 1] = T.base[o] + T.tiles_x[o] * T.tiles_y[o] * n_s;
+      T.base[o + 1] = T.base[o] + (in ? T.tiles_x[o] * T.tiles_y[o] * n_s : 0);
     }
-    if (T.base[P.n_octaves] > 0)
-    {
-      classify_kernel<<<T.base[P.n_octaves], dim3(32, 8), 0, st>>>(P, T, ep);
-      ++launches;
-    }
+    if (T.base[P.n_octaves] == 0)
+      return 0;
+    classify_kernel<<<T.base[P.n_octaves], dim3(32, 8), 0, st>>>(P, T, ep);
+    return 1;
+  }
+
+  // `classified_upto`: octaves below it were already classified (and the counters zeroed) by an
+  // earlier launch_classify on the same stream.
+  int launch_extrema(const PyramidDesc& P, const ExtremaParams& ep, int n_segments, int* seg_offsets,
+                     Candidate* cand, int cap_cand, Keypoint* ext_tmp, int classified_upto, int* scratch,
+                     Keypoint* ext, int cap_ext, Counters* counters, cudaStream_t st)
+  {
+    int launches = launch_classify(P, ep, n_segments, classified_upto, P.n_octaves, classified_upto == 0, st);
     // scratch layout: [chunk offsets (1024)] [keep flags cap_cand] [flag offsets cap_cand]
     int* chunk_off = scratch;
     int* keep = scratch + 1024;
