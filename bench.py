@@ -362,7 +362,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * F * W4K * H4K * 4,
                     "d2h_bytes_per_step": world * d2h[0],
                     "ms_per_step": 1e3 * max_e2e / args.steps},
-            "gpu_launches": int(launches_per_frame) * F * args.steps,
+            "gpu_launches": int(launches_per_frame) * F * args.steps * world,
             "clocks": clocks, "roofline": roofline, "stage_ms_per_frame": stage_ms, "cpu_baseline": cpu_baseline,
             "wall_s": wall,
         }
