@@ -87,7 +87,7 @@ typedef struct sara_b200_limits
 {
   int32_t max_width;       /* of the INPUT image */
   int32_t max_height;
-  int32_t max_keypoints;   /* per frame, <= 0 -> 262144 */
+  int32_t max_keypoints;   /* per frame, <= 0 -> 262144; at most 4194304 */
   int32_t num_slots;       /* frames in flight, <= 0 -> 1 */
   int32_t min_first_octave_index; /* most negative first_octave_index to size for (0 or -1) */
 } sara_b200_limits;
@@ -151,7 +151,8 @@ typedef enum sara_b200_pyramid_mode
   SARA_B200_PYRAMID_AUTO = 0,
   SARA_B200_PYRAMID_GENERIC = 1, /* one launch per scale, any tap count */
   SARA_B200_PYRAMID_STAGE = 2,   /* TMA-staged marching kernel, one launch per scale (default schedule) */
-  SARA_B200_PYRAMID_FUSED = 3    /* TMA-staged fused octave kernel, one launch per octave (default schedule) */
+  SARA_B200_PYRAMID_FUSED = 3,   /* TMA-staged fused octave kernel, one launch per octave (default schedule) */
+  SARA_B200_PYRAMID_MARCH = 4    /* TMA-staged scatter-form marching kernel, one launch per scale (default schedule) */
 } sara_b200_pyramid_mode;
 SARA_B200_API int sara_b200_set_pyramid_mode(sara_b200_ctx* ctx, int mode);
 /* Octave o + 1 only needs one scale of octave o, so by default the octaves of a frame overlap
@@ -175,6 +176,24 @@ SARA_B200_API int sara_b200_sift(sara_b200_ctx* ctx, const float* image, int w, 
                    const sara_b200_sift_args* args, sara_b200_keypoint* keypoints,
                    float* descriptors, int capacity, int* n_out);
 
+/* ---- frame ingest: from_rgb8_to_gray32f + compute_sift_keypoints --------------
+ * The video loop of the reference (cpp/examples/Sara/FeatureMatching/
+ * video_sift_matching.cpp:184-200) converts every decoded RGB8 frame with
+ * from_rgb8_to_gray32f (ImageProcessing/FastColorConversion.cpp:42-67) before
+ * compute_sift_keypoints.  These entry points take the 8-bit frame itself --
+ * `channels` = 3: interleaved RGB8 (ImageView<Rgb8>), 1: gray8 -- convert it on the
+ * device with the reference's arithmetic (bit-identical float image) and run the same
+ * chain, so a frame crosses PCIe as 3 or 1 bytes per pixel instead of 4.  A device-resident
+ * 8-bit frame (e.g. a decoder surface) must be 4-byte aligned. */
+SARA_B200_API int sara_b200_sift_u8(sara_b200_ctx* ctx, const uint8_t* image, int w, int h, int channels,
+                      int image_on_device, const sara_b200_sift_args* args, sara_b200_keypoint* keypoints,
+                      float* descriptors, int capacity, int* n_out);
+SARA_B200_API int sara_b200_sift_enqueue_u8(sara_b200_ctx* ctx, int slot, const uint8_t* image, int w, int h,
+                              int channels, int image_on_device, const sara_b200_sift_args* args, void* stream);
+/* The conversion alone (unit parity): host in, host out (w * h floats). */
+SARA_B200_API int sara_b200_to_gray32f(sara_b200_ctx* ctx, const uint8_t* src, int w, int h, int channels,
+                         float* dst);
+
 /* Asynchronous form: enqueue the whole frame on `slot`'s stream (or on
  * `stream`, a cudaStream_t passed as void*, when non-NULL) and return at once;
  * collect later.  A host `image` must stay valid until the matching collect. */
@@ -188,7 +207,8 @@ SARA_B200_API int sara_b200_collect(sara_b200_ctx* ctx, int slot, sara_b200_keyp
  * matcher): pointers stay valid until the slot is enqueued again. */
 SARA_B200_API int sara_b200_device_results(sara_b200_ctx* ctx, int slot, const sara_b200_keypoint** keypoints,
                              const float** descriptors, int* n_out);
-/* Waits for the slot's GPU work and reads back only the keypoint count. */
+/* Waits for the slot's GPU work and reads back only the keypoint count (clamped to the
+ * context capacity; OVERFLOW is returned when the frame exceeded it). */
 SARA_B200_API int sara_b200_wait(sara_b200_ctx* ctx, int slot, int* n_out);
 
 /* ---- ComputeDoGExtrema::operator() (DoG.hpp:116-131, DoG.cpp:23-87) --------

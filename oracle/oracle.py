@@ -119,6 +119,23 @@ class PyramidParams:
         )
 
 
+TRACE_FIELDS = 25  # x, y, s, o, type, iteration, H[9], g[3], lambda[3], h[3], decision
+
+
+def trace_refinement(on: bool) -> None:
+    """Starts (and clears) / stops the per-iteration trace of refine_extremum."""
+    lib().oracle_trace_refinement(int(on))
+
+
+def refinement_trace() -> np.ndarray:
+    """(n, 25) float32: one record per Newton iteration that reached the eigenvalue test."""
+    n = lib().oracle_trace_size()
+    out = np.zeros((n, TRACE_FIELDS), np.float32)
+    if n:
+        lib().oracle_trace_copy(_p(out))
+    return out
+
+
 def set_threading(mode: int, threads: int = 0) -> None:
     lib().oracle_set_threading(int(mode), int(threads))
 

@@ -601,6 +601,14 @@ namespace oracle {
     r[3 * 2 + 2] = cof(2, 2) * invdet;
   }
 
+  // Optional trace of every Newton iteration (tests/test_eigen_boundary_pin.py checks the
+  // Eigen-boundary restatements -- eigenvalue sign test, cofactor inverse -- against an
+  // independent float64 solver).  25 floats per record:
+  // x, y, s, o, type, iteration, H[9], g[3], lambda[3], h[3], decision
+  // (decision: 0 = "not definite": h = 0, stop; 1 = Newton step computed).
+  static bool g_trace_on = false;
+  static std::vector<float> g_trace;
+
   // FeatureDetectors/RefineExtremum.cpp:32-130 refine_extremum (3-D).
   // `type` arrives as the uint8 map value: 1 for maxima, 255 for minima (N2).
   bool refine_extremum(const Pyramid& I, int x, int y, int s, int o, int type,
@@ -628,9 +636,26 @@ namespace oracle {
       const float ft = float(type);
       const float lmax =
           std::max(std::max(lambda[0] * ft, lambda[1] * ft), lambda[2] * ft);
+      auto trace = [&](float decision) {
+        if (!g_trace_on)
+          return;
+        float rec[25] = {float(x), float(y), float(s), float(o), ft, float(i)};
+        for (int k = 0; k < 9; ++k)
+          rec[6 + k] = D_second[k];
+        for (int k = 0; k < 3; ++k)
+        {
+          rec[15 + k] = D_prime[k];
+          rec[18 + k] = lambda[k];
+          rec[21 + k] = h[k];
+        }
+        rec[24] = decision;
+#pragma omp critical(oracle_trace)
+        g_trace.insert(g_trace.end(), rec, rec + 25);
+      };
       if (lmax >= 0)
       {
         h[0] = h[1] = h[2] = 0.f;
+        trace(0.f);
         break;
       }
 
@@ -639,6 +664,7 @@ namespace oracle {
       for (int r = 0; r < 3; ++r)
         h[r] = ((-inv[3 * r + 0]) * D_prime[0] + (-inv[3 * r + 1]) * D_prime[1]) +
                (-inv[3 * r + 2]) * D_prime[2];
+      trace(1.f);
 
       if (std::max(std::abs(h[0]), std::abs(h[1])) > 1.5f)
         return false;
@@ -1251,10 +1277,12 @@ void oracle_set_threading(int mode, int threads)
   g_threads_pyramid = mode == 0 ? 1 : all;
 }
 
+// Threads the OpenMP stages actually use (the explicit count of oracle_set_threading,
+// which overrides OMP_NUM_THREADS; else the OpenMP default).
 int oracle_num_threads()
 {
 #ifdef _OPENMP
-  return omp_get_max_threads();
+  return g_threads_other > 0 ? g_threads_other : omp_get_max_threads();
 #else
   return 1;
 #endif
@@ -1440,6 +1468,21 @@ void oracle_sift_descriptor(const float* grad, int w, int h, float x, float y,
                             float s, float theta, int normalize, float* desc128)
 {
   sift_descriptor(x, y, s, theta, grad, w, h, 3.f, 0.2f, normalize != 0, desc128);
+}
+
+// Refinement trace (see g_trace): switch on, run oracle_dog_extrema / oracle_sift, read.
+void oracle_trace_refinement(int on)
+{
+  g_trace_on = on != 0;
+  g_trace.clear();
+}
+int oracle_trace_size()
+{
+  return static_cast<int>(g_trace.size() / 25);
+}
+void oracle_trace_copy(float* dst)
+{
+  std::memcpy(dst, g_trace.data(), g_trace.size() * sizeof(float));
 }
 
 // ---- whole pipeline ------------------------------------------------------ //

@@ -89,7 +89,7 @@ SYMBOLS = [
     "sara_b200_pyramid_enqueue", "sara_b200_num_octaves", "sara_b200_num_scales",
     "sara_b200_layer_size", "sara_b200_octave_scaling_factor", "sara_b200_copy_layer",
     "sara_b200_copy_extrema", "sara_b200_copy_oriented", "sara_b200_gaussian",
-    "sara_b200_make_gaussian_kernel",
+    "sara_b200_make_gaussian_kernel", "sara_b200_sift_u8", "sara_b200_sift_enqueue_u8", "sara_b200_to_gray32f",
 ]
 
 
@@ -125,6 +125,9 @@ def load_library() -> C.CDLL:
     L.sara_b200_last_timings.argtypes = [vp, C.c_int, C.POINTER(Timings)]
     L.sara_b200_sift.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(_SiftArgs), vp, vp, C.c_int, ip]
     L.sara_b200_sift_enqueue.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.POINTER(_SiftArgs), vp]
+    L.sara_b200_sift_u8.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_SiftArgs), vp, vp, C.c_int, ip]
+    L.sara_b200_sift_enqueue_u8.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_SiftArgs), vp]
+    L.sara_b200_to_gray32f.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp]
     L.sara_b200_collect.argtypes = [vp, C.c_int, vp, vp, C.c_int, ip]
     L.sara_b200_device_results.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), ip]
     L.sara_b200_wait.argtypes = [vp, C.c_int, ip]
@@ -249,8 +252,9 @@ class SiftContext:
                          edge_ratio_thres, int(extremum_refinement_iter))
 
     def set_pyramid_mode(self, mode):
-        """0 auto, 1 generic, 2 per-stage marching kernel, 3 fused octave kernel (same bits)."""
-        mode = {"auto": 0, "generic": 1, "stage": 2, "fused": 3}.get(mode, mode)
+        """0 auto, 1 generic, 2 gather-form stage kernel, 3 fused octave kernel, 4 scatter-form
+        marching kernel (same bits)."""
+        mode = {"auto": 0, "generic": 1, "stage": 2, "fused": 3, "march": 4}.get(mode, mode)
         self._check(self._L.sara_b200_set_pyramid_mode(self._ctx, int(mode)))
 
     def set_octave_overlap(self, on: bool):

@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsara_b200.so")
-SOURCES = ["ctx.cu", "pyramid.cu", "pyramid_fused.cu", "pyramid_stage.cu", "extrema.cu", "describe.cu"]
+SOURCES = ["ctx.cu", "ingest.cu", "pyramid.cu", "pyramid_fused.cu", "pyramid_stage.cu", "pyramid_march.cu", "extrema.cu", "describe.cu"]
 HEADERS = ["common.cuh", "scan.cuh", "fp32x2_tma.cuh", os.path.join("..", "..", "include", "sara_b200.h")]
 
 NVCC_FLAGS = [

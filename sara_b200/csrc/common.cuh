@@ -91,10 +91,20 @@ namespace sb {
   bool stage_kernel_supported(int n_taps);
   bool launch_stage(const float* src, int src_pitch, float* dst, float* dog, float* nextG, int w, int h,
                     int pitch, int nw, int nh, int npitch, const Taps& taps, cudaStream_t st);
+  // Marching scatter-form kernel (pyramid_march.cu): same contract as launch_stage, fewer fp32
+  // instructions (symmetric taps share their products) and no shared-memory window loads.
+  bool march_kernel_supported(const Taps& taps);
+  bool launch_march(const float* src, int src_pitch, float* dst, float* dog, float* nextG, int w, int h,
+                    int pitch, int nw, int nh, int npitch, const Taps& taps, cudaStream_t st);
   bool downscale_is_even_sampling(int sw, int sh, int dw, int dh);
   // All octaves from `first_octave` on in one single-CTA launch (pyramid.cu); 0 if not applicable.
   int launch_tail_octaves(const PyramidDesc& P, int first_octave, int downscale_index, const Taps* taps,
                           cudaStream_t st);
+
+  // Frame ingest (ingest.cu): 8-bit frames -> float32 gray on the device.
+  void fill_rgb_to_gray_lut(double* lut768);
+  void launch_rgb8_to_gray32f(const uint8_t* src, float* dst, int n_pixels, const double* d_lut, cudaStream_t st);
+  void launch_gray8_to_gray32f(const uint8_t* src, float* dst, int n_pixels, cudaStream_t st);
 
   struct ExtremaParams
   {

@@ -53,6 +53,7 @@ namespace {
     // geometry of the frame in flight / last frame
     PyramidDesc P{};
     float* d_img = nullptr;
+    uint8_t* d_u8 = nullptr;  // staging of an 8-bit host frame
     float* d_tmp = nullptr;
     int* seg_offsets = nullptr;
     int n_segments = 0;
@@ -65,7 +66,7 @@ namespace {
     cudaEvent_t ev[9] = {};  // [7], [8]: around the pyramid's longest launch
     double top_kernel_bytes = 0.;
     sara_b200_timings timings{};
-    int pyramid_launches = 0, total_launches = 0, extra_launches = 0;
+    int pyramid_launches = 0, total_launches = 0, extra_launches = 0, extra_launches_pre = 0;
   };
 
   }  // namespace
@@ -79,6 +80,9 @@ struct sara_b200_ctx
   int pyramid_mode = SARA_B200_PYRAMID_AUTO;
   bool octave_overlap = true;
   std::vector<Slot> slots;
+  double* d_gray_lut = nullptr;   // 3 x 256 products of the rgb -> gray conversion (ingest.cu)
+  float* scratch = nullptr;       // sara_b200_gaussian / sara_b200_to_gray32f work buffers (grown on demand)
+  size_t scratch_bytes = 0;
   char err[512] = "";
 };
 
@@ -222,8 +226,10 @@ namespace {
   }
 
   // Lays the pyramid, extremum maps and row counters out in the slot's arena.
+  // `need_f32`: the slot holds a float copy of the input (host float frames, all 8-bit frames);
+  // `u8_bytes`: staging for an 8-bit HOST frame.
   int layout_slot(sara_b200_ctx* ctx, Slot& S, int w, int h, const Geometry& g,
-                  const sara_b200_pyramid_params& pp, bool image_on_device)
+                  const sara_b200_pyramid_params& pp, bool need_f32, size_t u8_bytes = 0)
   {
     const int n_s = g.n_scales;
     const int n_ext_layers = std::max(n_s - 3, 0);
@@ -233,7 +239,8 @@ namespace {
       bytes = align_up(bytes + n, 256);
       return off;
     };
-    const size_t off_img = image_on_device ? 0 : take(sizeof(float) * w * h);
+    const size_t off_img = need_f32 ? take(sizeof(float) * w * h) : 0;
+    const size_t off_u8 = u8_bytes ? take(u8_bytes) : 0;
     const size_t off_tmp = g.pre_downscale > 0 ? take(sizeof(float) * w * h) : 0;
     size_t off_G[kMaxOctaves], off_D[kMaxOctaves], off_map[kMaxOctaves];
     int pitch[kMaxOctaves];
@@ -262,7 +269,8 @@ namespace {
       CU(ctx, cudaMalloc(&S.arena, bytes));
       S.arena_bytes = bytes;
     }
-    S.d_img = image_on_device ? nullptr : reinterpret_cast<float*>(S.arena + off_img);
+    S.d_img = need_f32 ? reinterpret_cast<float*>(S.arena + off_img) : nullptr;
+    S.d_u8 = u8_bytes ? reinterpret_cast<uint8_t*>(S.arena + off_u8) : nullptr;
     S.d_tmp = g.pre_downscale > 0 ? reinterpret_cast<float*>(S.arena + off_tmp) : nullptr;
     S.seg_offsets = reinterpret_cast<int*>(S.arena + off_segoff);
     S.n_segments = n_seg;
@@ -312,6 +320,23 @@ namespace {
     return 0;
   }
 
+  // Work buffer of the stand-alone building blocks (kept until the context is destroyed).
+  int grow_scratch(sara_b200_ctx* ctx, size_t bytes)
+  {
+    if (bytes <= ctx->scratch_bytes)
+      return 0;
+    if (ctx->scratch)
+    {
+      CU(ctx, cudaStreamSynchronize(ctx->slots[0].own_stream));
+      CU(ctx, cudaFree(ctx->scratch));
+      ctx->scratch = nullptr;
+      ctx->scratch_bytes = 0;
+    }
+    CU(ctx, cudaMalloc(&ctx->scratch, bytes));
+    ctx->scratch_bytes = bytes;
+    return 0;
+  }
+
   int check_slot(sara_b200_ctx* ctx, int slot)
   {
     if (!ctx)
@@ -325,27 +350,47 @@ namespace {
   // Gaussian pyramid + DoG pyramid of one frame.
   // `early`: extrema parameters when the caller goes on to the extrema stage; octave 0 is then
   // classified as soon as its own DoG layers exist, beside the smaller octaves still being built.
-  int enqueue_pyramid(sara_b200_ctx* ctx, Slot& S, const float* image, int w, int h, bool on_device,
+  // `u8_channels`: 0 for a float image; 1 (gray8) or 3 (interleaved RGB8) for an 8-bit frame,
+  // which is converted on the device first (ingest.cu).
+  int enqueue_pyramid(sara_b200_ctx* ctx, Slot& S, const void* image_any, int w, int h, bool on_device,
                       const sara_b200_pyramid_params& pp, float gauss_truncate, cudaStream_t st,
-                      const ExtremaParams* early = nullptr)
+                      const ExtremaParams* early = nullptr, int u8_channels = 0)
   {
+    const float* image = static_cast<const float*>(image_any);
     Geometry g;
     int rc = plan_geometry(ctx, w, h, pp, &g);
     if (rc)
       return rc;
-    rc = layout_slot(ctx, S, w, h, g, pp, on_device);
+    const size_t u8_bytes = static_cast<size_t>(w) * h * u8_channels;
+    rc = layout_slot(ctx, S, w, h, g, pp, !on_device || u8_channels > 0, on_device ? 0 : u8_bytes);
     if (rc)
       return rc;
     S.stream = st;
     S.pyramid_launches = 0;
     S.extra_launches = 0;
+    S.extra_launches_pre = 0;
     S.classified_upto = 0;
     S.top_kernel_bytes = 0.;
     const bool prof = ctx->profiling;
     if (prof)
       CU(ctx, cudaEventRecord(S.ev[0], st));
     const float* d_src = image;
-    if (!on_device)
+    if (u8_channels > 0)
+    {
+      const uint8_t* d_u8 = static_cast<const uint8_t*>(image_any);
+      if (!on_device)
+      {
+        CU(ctx, cudaMemcpyAsync(S.d_u8, image_any, u8_bytes, cudaMemcpyHostToDevice, st));
+        d_u8 = S.d_u8;
+      }
+      if (u8_channels == 3)
+        launch_rgb8_to_gray32f(d_u8, S.d_img, w * h, ctx->d_gray_lut, st);
+      else
+        launch_gray8_to_gray32f(d_u8, S.d_img, w * h, st);
+      ++S.extra_launches_pre;
+      d_src = S.d_img;
+    }
+    else if (!on_device)
     {
       CU(ctx, cudaMemcpyAsync(S.d_img, image, sizeof(float) * w * h, cudaMemcpyHostToDevice, st));
       d_src = S.d_img;
@@ -385,8 +430,12 @@ namespace {
         else if (g.pre_sigma > 0.f)
         {
           // fo == 0: base = gaussian(image, sqrt(s0^2 - s_cam^2)), GaussianPyramid.hpp:69-73
-          const bool fast = ctx->pyramid_mode != SARA_B200_PYRAMID_GENERIC && stage_kernel_supported(pre.n) &&
-                            launch_stage(d_src, w, o0.G, nullptr, nullptr, w, h, o0.pitch, 0, 0, 0, pre, st);
+          const int pm = ctx->pyramid_mode;
+          bool fast = false;
+          if ((pm == SARA_B200_PYRAMID_AUTO || pm == SARA_B200_PYRAMID_MARCH) && march_kernel_supported(pre))
+            fast = launch_march(d_src, w, o0.G, nullptr, nullptr, w, h, o0.pitch, 0, 0, 0, pre, st);
+          if (!fast && pm != SARA_B200_PYRAMID_GENERIC && stage_kernel_supported(pre.n))
+            fast = launch_stage(d_src, w, o0.G, nullptr, nullptr, w, h, o0.pitch, 0, 0, 0, pre, st);
           if (!fast)
             launch_gaussian_stage(d_src, w, o0.G, o0.pitch, nullptr, 0, w, h, pre, st);
         }
@@ -399,9 +448,16 @@ namespace {
       // other schedule runs on the generic kernel.
       const int mode = ctx->pyramid_mode;
       const bool fused = mode == SARA_B200_PYRAMID_FUSED && fused_octave_supported(S.stage_taps.data(), P.n_scales);
-      bool staged = (mode == SARA_B200_PYRAMID_AUTO || mode == SARA_B200_PYRAMID_STAGE) && P.n_scales > 1;
+      // The marching scatter-form kernel is the default; the older gather-form stage kernel stays
+      // selectable.  Both are "one launch per scale" and share the orchestration below.
+      bool marched = (mode == SARA_B200_PYRAMID_AUTO || mode == SARA_B200_PYRAMID_MARCH) && P.n_scales > 1;
+      for (int s = 1; s < P.n_scales && marched; ++s)
+        marched = march_kernel_supported(S.stage_taps[s]);
+      bool staged = !marched && (mode == SARA_B200_PYRAMID_AUTO || mode == SARA_B200_PYRAMID_STAGE) && P.n_scales > 1;
       for (int s = 1; s < P.n_scales && staged; ++s)
         staged = stage_kernel_supported(S.stage_taps[s].n);
+      const auto launch_inc = marched ? launch_march : launch_stage;
+      staged = staged || marched;
       const cudaStream_t main_st = st;
       bool side_used[3] = {false, false, false};
       for (int o = 0; o < P.n_octaves; ++o)
@@ -440,7 +496,7 @@ namespace {
               CU(ctx, cudaEventRecord(S.ev[7], st));
               S.top_kernel_bytes = 12.0 * oc.w * oc.h;  // reads G(s-1), writes G(s) and D(s-1): 3 x 4 B per pixel
             }
-            if (!launch_stage(oc.G + static_cast<size_t>(s - 1) * oc.layer_stride, oc.pitch,
+            if (!launch_inc(oc.G + static_cast<size_t>(s - 1) * oc.layer_stride, oc.pitch,
                               oc.G + static_cast<size_t>(s) * oc.layer_stride,
                               oc.D + static_cast<size_t>(s - 1) * oc.layer_stride, down ? next->G : nullptr, oc.w, oc.h,
                               oc.pitch, down ? next->w : 0, down ? next->h : 0, down ? next->pitch : 0, S.stage_taps[s],
@@ -467,7 +523,8 @@ namespace {
             }
             CU(ctx, cudaEventRecord(S.ev_down[o], st));
           }
-          if (o == 0 && early != nullptr && ctx->octave_overlap && P.n_octaves > 1 && P.n_scales >= 4 &&
+          // (not under profiling: the stage timings must not overlap)
+          if (o == 0 && early != nullptr && !prof && ctx->octave_overlap && P.n_octaves > 1 && P.n_scales >= 4 &&
               S.n_segments > 0)
           {
             // octave 0 is complete on this stream: classify it now (its DoG layers are still in L2)
@@ -523,7 +580,7 @@ namespace {
     if (prof)
       CU(ctx, cudaEventRecord(S.ev[2], st));
     CU(ctx, cudaGetLastError());
-    S.total_launches = S.pyramid_launches + S.extra_launches;
+    S.total_launches = S.pyramid_launches + S.extra_launches + S.extra_launches_pre;
     return 0;
   }
 
@@ -689,9 +746,12 @@ int sara_b200_create(int device, const sara_b200_limits* limits, sara_b200_ctx**
   auto* ctx = new sara_b200_ctx;
   ctx->device = device;
   ctx->lim = *limits;
+  if (limits->max_keypoints > (1 << 22))
+  {
+    delete ctx;
+    return fail(nullptr, SARA_B200_ERR_BAD_ARG, "limits: max_keypoints must be <= %d", 1 << 22);
+  }
   ctx->cap_kp = limits->max_keypoints > 0 ? limits->max_keypoints : 262144;
-  if (ctx->cap_kp > 500000)
-    ctx->cap_kp = 500000;
   ctx->cap_ext = ctx->cap_kp;
   ctx->cap_cand = 2 * ctx->cap_kp;
   const int n_slots = limits->num_slots > 0 ? limits->num_slots : 1;
@@ -757,7 +817,8 @@ int sara_b200_create(int device, const sara_b200_limits* limits, sara_b200_ctx**
     Geometry g;
     if (plan_geometry(ctx, limits->max_width, limits->max_height, pp, &g) == 0)
     {
-      const int rc = layout_slot(ctx, S, limits->max_width, limits->max_height, g, pp, false);
+      const int rc = layout_slot(ctx, S, limits->max_width, limits->max_height, g, pp, true,
+                                 static_cast<size_t>(3) * limits->max_width * limits->max_height);
       if (rc)
       {
         std::memcpy(g_create_error, ctx->err, sizeof(g_create_error));
@@ -766,6 +827,19 @@ int sara_b200_create(int device, const sara_b200_limits* limits, sara_b200_ctx**
       }
     }
     S.P = PyramidDesc{};
+  }
+  {
+    double lut[768];
+    fill_rgb_to_gray_lut(lut);
+    cudaError_t err = cudaMalloc(&ctx->d_gray_lut, sizeof(lut));
+    if (err == cudaSuccess)
+      err = cudaMemcpy(ctx->d_gray_lut, lut, sizeof(lut), cudaMemcpyHostToDevice);
+    if (err != cudaSuccess)
+    {
+      const int code = fail(nullptr, SARA_B200_ERR_CUDA, "context creation failed: %s", cudaGetErrorString(err));
+      sara_b200_destroy(ctx);
+      return code;
+    }
   }
   *out = ctx;
   return 0;
@@ -803,6 +877,8 @@ void sara_b200_destroy(sara_b200_ctx* ctx)
     if (S.own_stream)
       cudaStreamDestroy(S.own_stream);
   }
+  cudaFree(ctx->d_gray_lut);
+  cudaFree(ctx->scratch);
   delete ctx;
 }
 
@@ -835,7 +911,7 @@ int sara_b200_set_pyramid_mode(sara_b200_ctx* ctx, int mode)
 {
   if (!ctx)
     return SARA_B200_ERR_BAD_ARG;
-  if (mode < SARA_B200_PYRAMID_AUTO || mode > SARA_B200_PYRAMID_FUSED)
+  if (mode < SARA_B200_PYRAMID_AUTO || mode > SARA_B200_PYRAMID_MARCH)
     return fail(ctx, SARA_B200_ERR_BAD_ARG, "unknown pyramid mode %d", mode);
   ctx->pyramid_mode = mode;
   return 0;
@@ -860,14 +936,19 @@ int sara_b200_last_timings(sara_b200_ctx* ctx, int slot, sara_b200_timings* out)
   return 0;
 }
 
-int sara_b200_sift_enqueue(sara_b200_ctx* ctx, int slot, const float* image, int w, int h,
-                           int image_on_device, const sara_b200_sift_args* args, void* stream)
+static int sift_enqueue_impl(sara_b200_ctx* ctx, int slot, const void* image, int w, int h, int image_on_device,
+                             const sara_b200_sift_args* args, void* stream, int u8_channels)
 {
   int rc = check_slot(ctx, slot);
   if (rc)
     return rc;
   if (!image || !args)
     return fail(ctx, SARA_B200_ERR_BAD_ARG, "null argument");
+  if (u8_channels != 0 && u8_channels != 1 && u8_channels != 3)
+    return fail(ctx, SARA_B200_ERR_BAD_ARG, "8-bit frames have 1 (gray) or 3 (interleaved RGB) channels, got %d",
+                u8_channels);
+  if (u8_channels > 0 && image_on_device && (reinterpret_cast<uintptr_t>(image) & 3) != 0)
+    return fail(ctx, SARA_B200_ERR_BAD_ARG, "a device-resident 8-bit frame must be 4-byte aligned");
   Slot& S = ctx->slots[slot];
   if (S.busy)
     return fail(ctx, SARA_B200_ERR_BUSY, "slot %d holds an un-collected frame", slot);
@@ -881,8 +962,8 @@ int sara_b200_sift_enqueue(sara_b200_ctx* ctx, int slot, const float* image, int
     return fail(ctx, SARA_B200_ERR_BAD_ARG,
                 "img_padding_sz must be >= 1 (the 3x3x3 neighbourhood must stay inside the layer)");
   const ExtremaParams early{args->extremum_thres, args->edge_ratio_thres, args->extremum_refinement_iter, 5};
-  rc = enqueue_pyramid(ctx, S, image, w, h, image_on_device != 0, args->pyramid_params,
-                       args->gauss_truncate, st, &early);
+  rc = enqueue_pyramid(ctx, S, image, w, h, image_on_device != 0, args->pyramid_params, args->gauss_truncate, st,
+                       &early, u8_channels);
   if (rc)
     return rc;
   // Quirk N1 (SIFT.cpp:45-51 vs DoG.hpp:72-78): extremum_refinement_iter lands in
@@ -898,6 +979,21 @@ int sara_b200_sift_enqueue(sara_b200_ctx* ctx, int slot, const float* image, int
   return finish_enqueue(ctx, S, st);
 }
 
+int sara_b200_sift_enqueue(sara_b200_ctx* ctx, int slot, const float* image, int w, int h,
+                           int image_on_device, const sara_b200_sift_args* args, void* stream)
+{
+  return sift_enqueue_impl(ctx, slot, image, w, h, image_on_device, args, stream, 0);
+}
+
+int sara_b200_sift_enqueue_u8(sara_b200_ctx* ctx, int slot, const uint8_t* image, int w, int h, int channels,
+                              int image_on_device, const sara_b200_sift_args* args, void* stream)
+{
+  if (channels != 1 && channels != 3)
+    return fail(ctx, SARA_B200_ERR_BAD_ARG, "8-bit frames have 1 (gray) or 3 (interleaved RGB) channels, got %d",
+                channels);
+  return sift_enqueue_impl(ctx, slot, image, w, h, image_on_device, args, stream, channels);
+}
+
 int sara_b200_wait(sara_b200_ctx* ctx, int slot, int* n_out)
 {
   int rc = check_slot(ctx, slot);
@@ -907,8 +1003,13 @@ int sara_b200_wait(sara_b200_ctx* ctx, int slot, int* n_out)
   rc = wait_slot(ctx, S);
   if (rc)
     return rc;
+  const Counters c = *S.h_counters;
   if (n_out)
-    *n_out = S.has_keypoints ? S.h_counters->n_kp : 0;
+    *n_out = S.has_keypoints ? std::min(c.n_kp, ctx->cap_kp) : 0;
+  if (c.overflow)
+    return fail(ctx, SARA_B200_ERR_OVERFLOW,
+                "frame exceeds the context capacity (candidates %d, extrema %d, keypoints %d; max_keypoints %d)",
+                c.n_cand, c.n_ext, c.n_kp, ctx->cap_kp);
   return 0;
 }
 
@@ -967,6 +1068,16 @@ int sara_b200_sift(sara_b200_ctx* ctx, const float* image, int w, int h, int ima
                    int capacity, int* n_out)
 {
   int rc = sara_b200_sift_enqueue(ctx, 0, image, w, h, image_on_device, args, nullptr);
+  if (rc)
+    return rc;
+  return sara_b200_collect(ctx, 0, keypoints, descriptors, capacity, n_out);
+}
+
+int sara_b200_sift_u8(sara_b200_ctx* ctx, const uint8_t* image, int w, int h, int channels, int image_on_device,
+                      const sara_b200_sift_args* args, sara_b200_keypoint* keypoints, float* descriptors,
+                      int capacity, int* n_out)
+{
+  int rc = sara_b200_sift_enqueue_u8(ctx, 0, image, w, h, channels, image_on_device, args, nullptr);
   if (rc)
     return rc;
   return sara_b200_collect(ctx, 0, keypoints, descriptors, capacity, n_out);
@@ -1123,24 +1234,42 @@ int sara_b200_gaussian(sara_b200_ctx* ctx, const float* src, int w, int h, float
   if (make_taps(sigma, gauss_truncate, &taps) < 0)
     return fail(ctx, SARA_B200_ERR_BAD_ARG, "Gaussian kernel exceeds %d taps", kMaxTaps);
   CU(ctx, cudaSetDevice(ctx->device));
-  float *d_a = nullptr, *d_b = nullptr;
   const size_t bytes = sizeof(float) * w * h;
-  CU(ctx, cudaMalloc(&d_a, bytes));
-  cudaError_t e = cudaMalloc(&d_b, bytes);
-  if (e != cudaSuccess)
-  {
-    cudaFree(d_a);
-    return fail(ctx, SARA_B200_ERR_OOM, "cudaMalloc failed: %s", cudaGetErrorString(e));
-  }
+  int rc = grow_scratch(ctx, 2 * align_up(bytes, 256));
+  if (rc)
+    return rc;
+  float* d_a = ctx->scratch;
+  float* d_b = reinterpret_cast<float*>(reinterpret_cast<char*>(ctx->scratch) + align_up(bytes, 256));
   cudaStream_t st = ctx->slots[0].own_stream;
-  cudaMemcpyAsync(d_a, src, bytes, cudaMemcpyHostToDevice, st);
+  CU(ctx, cudaMemcpyAsync(d_a, src, bytes, cudaMemcpyHostToDevice, st));
   launch_gaussian_stage(d_a, w, d_b, w, nullptr, 0, w, h, taps, st);
-  cudaMemcpyAsync(dst, d_b, bytes, cudaMemcpyDeviceToHost, st);
-  e = cudaStreamSynchronize(st);
-  cudaFree(d_a);
-  cudaFree(d_b);
-  if (e != cudaSuccess)
-    return fail(ctx, SARA_B200_ERR_CUDA, "gaussian failed: %s", cudaGetErrorString(e));
+  CU(ctx, cudaMemcpyAsync(dst, d_b, bytes, cudaMemcpyDeviceToHost, st));
+  CU(ctx, cudaStreamSynchronize(st));
+  return 0;
+}
+
+int sara_b200_to_gray32f(sara_b200_ctx* ctx, const uint8_t* src, int w, int h, int channels, float* dst)
+{
+  if (!ctx)
+    return fail(nullptr, SARA_B200_ERR_BAD_ARG, "null context");
+  if (!src || !dst || w <= 0 || h <= 0 || (channels != 1 && channels != 3))
+    return fail(ctx, SARA_B200_ERR_BAD_ARG, "to_gray32f: bad arguments");
+  CU(ctx, cudaSetDevice(ctx->device));
+  const size_t n = static_cast<size_t>(w) * h;
+  const size_t in_bytes = align_up(n * channels, 256);
+  int rc = grow_scratch(ctx, in_bytes + sizeof(float) * n);
+  if (rc)
+    return rc;
+  uint8_t* d_in = reinterpret_cast<uint8_t*>(ctx->scratch);
+  float* d_out = reinterpret_cast<float*>(reinterpret_cast<char*>(ctx->scratch) + in_bytes);
+  cudaStream_t st = ctx->slots[0].own_stream;
+  CU(ctx, cudaMemcpyAsync(d_in, src, n * channels, cudaMemcpyHostToDevice, st));
+  if (channels == 3)
+    launch_rgb8_to_gray32f(d_in, d_out, static_cast<int>(n), ctx->d_gray_lut, st);
+  else
+    launch_gray8_to_gray32f(d_in, d_out, static_cast<int>(n), st);
+  CU(ctx, cudaMemcpyAsync(dst, d_out, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+  CU(ctx, cudaStreamSynchronize(st));
   return 0;
 }
 

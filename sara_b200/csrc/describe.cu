@@ -417,8 +417,14 @@ namespace sb {
         const int side = 2 * rounded_r + 1;
         const int count = side * side;
         int q_n = 0;  // entries waiting in the queue (< 96 between rounds)
-        // lane's pixel of the bounding square, advanced by 32 per round (side >= 35 > 32)
+        // lane's pixel of the bounding square, advanced by 32 per round.  `side` can be smaller
+        // than a warp (refined sigma < 1.46 <=> rounded_r <= 15), so wrapping takes a loop.
         int u = lane - rounded_r, v = -rounded_r;
+        while (u > rounded_r)
+        {
+          u -= side;
+          ++v;
+        }
         for (int t0 = 0; t0 < count; t0 += 32)
         {
           const int t = t0 + lane;
@@ -434,7 +440,7 @@ namespace sb {
             uv = (u & 0xffff) | (v << 16);
           }
           u += 32;
-          if (u > rounded_r)
+          while (u > rounded_r)
           {
             u -= side;
             ++v;

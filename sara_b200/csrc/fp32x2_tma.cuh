@@ -16,6 +16,14 @@ namespace sb {
       asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
       return r;
     }
+    // Same, but never re-materialised: ptxas otherwise repeats the two register moves in front
+    // of every packed instruction that reads the pair.
+    __device__ __forceinline__ u64 pack2_once(float lo, float hi)
+    {
+      u64 r;
+      asm volatile("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+      return r;
+    }
     __device__ __forceinline__ float lo2(u64 v) { return __uint_as_float(static_cast<unsigned>(v)); }
     __device__ __forceinline__ float hi2(u64 v) { return __uint_as_float(static_cast<unsigned>(v >> 32)); }
     __device__ __forceinline__ u64 mul2(u64 a, u64 b)

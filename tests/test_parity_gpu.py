@@ -82,27 +82,39 @@ def wide_ctx():
 # Sizes that exercise the fused octave kernel's strips and segments: several strips
 # of both tile widths, odd widths/heights (ragged last strip, straddling column
 # pair), segment seams, and images narrower than the cascade halo.
+@pytest.mark.parametrize("mode", ["stage", "fused", "auto"])
 @pytest.mark.parametrize("w,h", [(1300, 420), (1281, 333), (2000, 300), (1025, 1100), (1920, 1080),
                                  (129, 700), (257, 97), (90, 1000), (1000, 41), (31, 31)])
-def test_fused_octave_bit_exact(wide_ctx, w, h):
+def test_pyramid_kernels_bit_exact_on_ragged_shapes(wide_ctx, w, h, mode):
+    """Every pyramid implementation, selected EXPLICITLY, on shapes that hit strip / segment
+    seams, ragged last strips and images narrower than the cascade halo."""
     img = S.tex(w, h, 7)
     p_gpu, p_ref = _pp(0)
     ref = O.compute_dog_extrema(img, p_ref)
-    wide_ctx.pyramid_enqueue(0, img, p_gpu)
-    wide_ctx.wait(0)
-    assert_pyramids_identical(wide_ctx, ref)
-
-
-def test_fused_octave_noise_and_negative_values(wide_ctx):
-    # white noise (every tap matters) and signed data (signed zeros / cancellation)
-    rng = np.random.default_rng(5)
-    for img in (rng.random((300, 1111), dtype=np.float32),
-                (rng.standard_normal((257, 640)) * 3).astype(np.float32)):
-        p_gpu, p_ref = _pp(0)
-        ref = O.compute_dog_extrema(img, p_ref)
+    wide_ctx.set_pyramid_mode(mode)
+    try:
         wide_ctx.pyramid_enqueue(0, img, p_gpu)
         wide_ctx.wait(0)
         assert_pyramids_identical(wide_ctx, ref)
+    finally:
+        wide_ctx.set_pyramid_mode("auto")
+
+
+@pytest.mark.parametrize("mode", ["stage", "fused", "auto"])
+def test_pyramid_kernels_noise_and_negative_values(wide_ctx, mode):
+    # white noise (every tap matters) and signed data (signed zeros / cancellation)
+    rng = np.random.default_rng(5)
+    wide_ctx.set_pyramid_mode(mode)
+    try:
+        for img in (rng.random((300, 1111), dtype=np.float32),
+                    (rng.standard_normal((257, 640)) * 3).astype(np.float32)):
+            p_gpu, p_ref = _pp(0)
+            ref = O.compute_dog_extrema(img, p_ref)
+            wide_ctx.pyramid_enqueue(0, img, p_gpu)
+            wide_ctx.wait(0)
+            assert_pyramids_identical(wide_ctx, ref)
+    finally:
+        wide_ctx.set_pyramid_mode("auto")
 
 
 def test_pyramid_other_schedules(ctx):
@@ -227,6 +239,8 @@ def test_capacity_overflow_is_reported():
     (dict(scale_count_per_octave=7, scale_geometric_factor=float(np.float32(2.0) ** np.float32(0.25))), {}),
     (dict(num_octaves_max=3), dict(extremum_thres=0.02, edge_ratio_thres=5.0)),
     (dict(), dict(extremum_thres=0.003, extremum_refinement_iter=2)),
+    (dict(scale_initial=0.8), {}), (dict(scale_initial=1.0), {}), (dict(scale_initial=1.2), {}),
+    (dict(scale_initial=1.0, scale_camera=0.25), dict(extremum_thres=0.005)),
 ])
 def test_sift_other_parameters(ctx, kw, args):
     img = S.tex(512, 384, 91)
@@ -241,6 +255,52 @@ def test_sift_other_parameters(ctx, kw, args):
     assert_extrema_identical(ctx.extrema(), ref.extrema)
     assert len(ref.keypoints) > 20
     compare_keypoints(kl.features, kl.descriptors, ref.keypoints, ref.descriptors)
+
+
+@pytest.mark.parametrize("fo,s0", [(0, 1.0), (-1, 1.0), (0, 0.8), (-1, 1.6)])
+def test_descriptors_of_small_scale_keypoints(ctx, fo, s0):
+    """Keypoints whose descriptor window is narrower than a warp (round(10.6 sigma) <= 15, i.e.
+    refined sigma < 1.46): EVERY one of them must be inside the descriptor tolerance (the
+    window walk of descriptor_kernel used to assume side >= 33)."""
+    img = S.tex(640, 480, 123)
+    p_gpu, p_ref = _pp(fo, scale_initial=s0)
+    ref = O.compute_sift_keypoints(img, p_ref, parallel=True)
+    kl = ctx.compute_sift_keypoints(img, p_gpu)
+    assert_extrema_identical(ctx.extrema(), ref.extrema)
+    from parity import match_oriented, DESC_REL, DESC_ABS
+
+    ko_gpu, ko_ref = ctx.oriented(), ref.oriented
+    ig, ir, bad, n_ext = match_oriented(ko_gpu, ko_ref)
+    sigma = 1.0 / np.sqrt(ko_ref["shape"][ir, 0])
+    small = sigma < 1.46
+    if s0 <= 1.0:
+        assert small.sum() > 100, small.sum()
+    if small.sum() == 0:
+        return
+    dth = np.abs(ko_gpu["orientation"][ig] - ko_ref["orientation"][ir])
+    dth = np.minimum(dth, 2 * np.pi - dth)
+    da, db = kl.descriptors[ig].astype(np.float64), ref.descriptors[ir].astype(np.float64)
+    err = np.linalg.norm(da - db, axis=1)
+    tol = DESC_REL * np.linalg.norm(db, axis=1) + DESC_ABS
+    ok = (err <= tol) | (dth > 1e-3)
+    assert ok[small].all(), f"{(~ok[small]).sum()} of {small.sum()} small-scale descriptors off, max {err[small].max()}"
+
+
+@pytest.mark.parametrize("i", [0, 7, 100])
+def test_c4_sequence_frames_vs_oracle(i):
+    """Configs C4 / C5: frames of the translated-scene sequence, full SIFT against the oracle."""
+    img = S.sequence_frame(1920, 1080, i)
+    c = sb.SiftContext(1920, 1080, max_keypoints=65536, min_first_octave_index=0)
+    try:
+        p_gpu, p_ref = _pp(0)
+        ref = O.compute_sift_keypoints(img, p_ref, parallel=True)
+        kl = c.compute_sift_keypoints(img, p_gpu)
+        assert_pyramids_identical(c, ref)
+        assert_extrema_identical(c.extrema(), ref.extrema)
+        assert len(ref.keypoints) > 1000
+        print(compare_keypoints(kl.features, kl.descriptors, ref.keypoints, ref.descriptors))
+    finally:
+        c.close()
 
 
 @pytest.mark.parametrize("w,h", [(2000, 40), (40, 1500), (641, 479), (1023, 767)])
