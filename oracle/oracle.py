@@ -119,6 +119,22 @@ class PyramidParams:
         )
 
 
+def rgb8_to_gray32f(rgb) -> np.ndarray:
+    """from_rgb8_to_gray32f (FastColorConversion.cpp:42-67, non-Halide branch): HxWx3 uint8 -> HxW float32."""
+    a = np.ascontiguousarray(rgb, dtype=np.uint8)
+    assert a.ndim == 3 and a.shape[2] == 3
+    out = np.empty(a.shape[:2], np.float32)
+    lib().oracle_rgb8_to_gray32f(a.ctypes.data_as(C.c_void_p), a.shape[0] * a.shape[1], _p(out))
+    return out
+
+
+def gray8_to_gray32f(gray) -> np.ndarray:
+    a = np.ascontiguousarray(gray, dtype=np.uint8)
+    out = np.empty(a.shape, np.float32)
+    lib().oracle_gray8_to_gray32f(a.ctypes.data_as(C.c_void_p), a.size, _p(out))
+    return out
+
+
 TRACE_FIELDS = 25  # x, y, s, o, type, iteration, H[9], g[3], lambda[3], h[3], decision
 
 

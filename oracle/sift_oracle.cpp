@@ -1470,6 +1470,40 @@ void oracle_sift_descriptor(const float* grad, int w, int h, float x, float y,
   sift_descriptor(x, y, s, theta, grad, w, h, 3.f, 0.2f, normalize != 0, desc128);
 }
 
+// from_rgb8_to_gray32f, non-Halide branch (ImageProcessing/FastColorConversion.cpp:42-67):
+// DO::Sara::convert(ImageView<Rgb8>, ImageView<float>) = per pixel smart_convert_color
+// (Core/Pixel/SmartColorConversion.hpp:237-246): each channel to double with
+// to_normalized_float_channel<uint8_t, double> (Core/Pixel/ChannelConversion.hpp:41-53),
+// rgb_to_gray<double> (Core/Pixel/ColorConversion.hpp:27-33), then narrowed to float
+// (ChannelConversion.hpp:79-82).
+void oracle_rgb8_to_gray32f(const unsigned char* src, int n_pixels, float* dst)
+{
+  for (int i = 0; i < n_pixels; ++i)
+  {
+    double rgb[3];
+    for (int c = 0; c < 3; ++c)
+    {
+      const double float_min = 0.0, float_max = 255.0;
+      const double float_range = float_max - float_min;
+      rgb[c] = (static_cast<double>(src[3 * i + c]) - float_min) / float_range;
+    }
+    const double gray = 0.2125 * rgb[0] + 0.7154 * rgb[1] + 0.0721 * rgb[2];
+    dst[i] = static_cast<float>(gray);
+  }
+}
+
+// ImageView<uint8_t> -> float: convert_channel(Int, float&) = to_normalized_float_channel
+// <uint8_t, float> (Core/Pixel/ChannelConversion.hpp:41-53, 95-99).
+void oracle_gray8_to_gray32f(const unsigned char* src, int n_pixels, float* dst)
+{
+  for (int i = 0; i < n_pixels; ++i)
+  {
+    const float float_min = 0.f, float_max = 255.f;
+    const float float_range = float_max - float_min;
+    dst[i] = (static_cast<float>(src[i]) - float_min) / float_range;
+  }
+}
+
 // Refinement trace (see g_trace): switch on, run oracle_dog_extrema / oracle_sift, read.
 void oracle_trace_refinement(int on)
 {

@@ -215,6 +215,20 @@ def _as_image(image):
     return a.ctypes.data, int(a.shape[1]), int(a.shape[0]), False, a
 
 
+def _as_u8_image(image):
+    """Returns (pointer, w, h, channels, on_device, keepalive) of an 8-bit frame."""
+    if hasattr(image, "data_ptr"):  # torch tensor
+        t = image
+        if str(t.dtype) != "torch.uint8" or not t.is_contiguous() or t.dim() not in (2, 3) or \
+                (t.dim() == 3 and t.shape[2] != 3):
+            raise ValueError("8-bit frame tensor must be contiguous uint8, HxW or HxWx3")
+        return t.data_ptr(), int(t.shape[1]), int(t.shape[0]), 3 if t.dim() == 3 else 1, bool(t.is_cuda), t
+    a = np.ascontiguousarray(image, dtype=np.uint8)
+    if a.ndim not in (2, 3) or (a.ndim == 3 and a.shape[2] != 3):
+        raise ValueError("8-bit frame must be HxW or HxWx3 uint8")
+    return a.ctypes.data, int(a.shape[1]), int(a.shape[0]), 3 if a.ndim == 3 else 1, False, a
+
+
 class SiftContext:
     """One GPU context (see the threading contract in include/sara_b200.h)."""
 
@@ -273,9 +287,39 @@ class SiftContext:
         ptr, w, h, on_dev, keep = _as_image(image)
         args = self._sift_args(pyramid_params, gauss_truncate, extremum_thres, edge_ratio_thres,
                                extremum_refinement_iter)
-        self._keep[slot] = keep
         self._check(self._L.sara_b200_sift_enqueue(self._ctx, slot, ptr, w, h, int(on_dev), C.byref(args),
                                                    C.c_void_p(stream) if stream else None))
+        self._keep[slot] = keep  # only once the enqueue succeeded: a BUSY slot keeps its own frame alive
+
+    def enqueue_u8(self, slot, image, pyramid_params=None, gauss_truncate=4.0, extremum_thres=0.01,
+                   edge_ratio_thres=10.0, extremum_refinement_iter=5, stream=None):
+        """8-bit frame in: HxW (gray8) or HxWx3 (interleaved RGB8); converted on the device as
+        from_rgb8_to_gray32f / ImageView<uint8_t>::convert<float>() would (FastColorConversion.cpp:42-67)."""
+        ptr, w, h, ch, on_dev, keep = _as_u8_image(image)
+        args = self._sift_args(pyramid_params, gauss_truncate, extremum_thres, edge_ratio_thres,
+                               extremum_refinement_iter)
+        self._check(self._L.sara_b200_sift_enqueue_u8(self._ctx, slot, ptr, w, h, ch, int(on_dev), C.byref(args),
+                                                      C.c_void_p(stream) if stream else None))
+        self._keep[slot] = keep
+
+    def enqueue_raw_u8(self, slot, ptr, w, h, channels, on_device, args, stream=None):
+        self._check(self._L.sara_b200_sift_enqueue_u8(self._ctx, slot, ptr, w, h, channels, int(on_device),
+                                                      C.byref(args), C.c_void_p(stream) if stream else None))
+
+    def compute_sift_keypoints_u8(self, image, pyramid_params=None, gauss_truncate=4.0, extremum_thres=0.01,
+                                  edge_ratio_thres=10.0, extremum_refinement_iter=5) -> KeypointList:
+        self.enqueue_u8(0, image, pyramid_params, gauss_truncate, extremum_thres, edge_ratio_thres,
+                        extremum_refinement_iter)
+        return self.collect(0)
+
+    def to_gray32f(self, image) -> np.ndarray:
+        a = np.ascontiguousarray(image, dtype=np.uint8)
+        if a.ndim not in (2, 3) or (a.ndim == 3 and a.shape[2] != 3):
+            raise ValueError("image must be HxW or HxWx3 uint8")
+        out = np.empty(a.shape[:2], np.float32)
+        self._check(self._L.sara_b200_to_gray32f(self._ctx, a.ctypes.data, a.shape[1], a.shape[0],
+                                                 3 if a.ndim == 3 else 1, out.ctypes.data))
+        return out
 
     def enqueue_raw(self, slot, ptr, w, h, on_device, args, stream=None):
         self._check(self._L.sara_b200_sift_enqueue(self._ctx, slot, ptr, w, h, int(on_device), C.byref(args),
@@ -311,9 +355,9 @@ class SiftContext:
     def pyramid_enqueue(self, slot, image, pyramid_params=None, gauss_truncate=4.0, stream=None):
         ptr, w, h, on_dev, keep = _as_image(image)
         pp = (pyramid_params or ImagePyramidParams())._c()
-        self._keep[slot] = keep
         self._check(self._L.sara_b200_pyramid_enqueue(self._ctx, slot, ptr, w, h, int(on_dev), C.byref(pp),
                                                       gauss_truncate, C.c_void_p(stream) if stream else None))
+        self._keep[slot] = keep
 
     # ---- ComputeDoGExtrema ------------------------------------------------------------
     def dog_extrema(self, image, pyramid_params=None, gauss_truncate=4.0, extremum_thres=0.01,

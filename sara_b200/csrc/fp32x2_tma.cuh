@@ -78,6 +78,21 @@ namespace sb {
     }
 
 
+    // ---- cp.async (LDGSTS): 8-byte global -> shared copies, completion by commit groups -----
+    __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc)
+    {
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+    }
+    __device__ __forceinline__ void cp_async_commit()
+    {
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    template <int N>
+    __device__ __forceinline__ void cp_async_wait()
+    {
+      asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+    }
+
     // Driver entry point of cuTensorMapEncodeTiled (no link-time dependency on libcuda).
     typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

@@ -29,19 +29,21 @@
 //    streams (two columns 32 apart), the taps are scalar (uniform-register) operands.
 //    RN(acc + p) is issued as fma.rn.f32x2(acc, ONE, p), see fp32x2_tma.cuh.
 //
-//  CTA = strip of TX = 64 NW output columns x a segment of rows, marching down in blocks
-//  of 32 rows.  Per block:
+//  CTA (128 threads) = strip of 248 output columns x a segment of rows, marching down in
+//  blocks of 32 rows.  Per block:
 //   1. TMA (cp.async.bulk.tensor.2d + mbarrier, double buffered, two blocks ahead) stages
-//      32 rows x (128 + 2c) columns per region of 128 output columns; out-of-image columns
-//      of the first / last strip are overwritten with the replicated border pixel
+//      32 rows x (124 + 2c) columns for each half of the strip; out-of-image columns of the
+//      first / last strip are overwritten with the replicated border pixel
 //      (LinearFiltering.hpp:95-100).
-//   2. Row pass: lane = row of the block, a warp owns 64 output columns as two packed runs
-//      of 32; fully unrolled, so only the products and sums that exist are issued
-//      (triangular ramp-up / ramp-down at the run ends).  Output -> F (row-filtered block).
-//   3. Column pass: a thread owns two columns (32 apart) for the whole segment; 2c sums in
+//   2. Row pass: a warp owns 8 rows, a lane one row and one of its four runs of 31 output
+//      columns in BOTH half strips (the two halves of its f32x2 registers); fully unrolled,
+//      so only the products and sums that exist are issued (triangular ramp-up / ramp-down
+//      at the run ends).  Output -> F (row-filtered block).
+//   3. Column pass: a thread owns two adjacent columns for the whole segment; 2c sums in
 //      flight shift down one slot per row; rows outside the image replicate the border row
 //      (LinearFiltering.hpp:137-142) by feeding F's first / last row again.  Epilogue:
-//      G(s), D(s-1) (G(s-1) re-read through L2, prefetched four rows ahead), next octave.
+//      G(s), D(s-1) (G(s-1) re-read through L2, prefetched eight rows ahead), next octave;
+//      8-byte stores.
 #include <cstdlib>
 #include <cstring>
 
@@ -54,14 +56,16 @@ namespace sb {
 
     using namespace fused;
 
-    constexpr int R = 32;   // rows per block = lanes of a row-pass warp
-    constexpr int T = 32;   // outputs of one packed run in the row pass
-    constexpr int WC = 64;  // output columns per warp
-    constexpr int PD = 4;   // prefetch distance (rows) of G(s-1) in the column pass
+    constexpr int R = 32;   // rows per block: 4 warps x 8 rows in the row pass
+    constexpr int T = 31;   // outputs of one run of the row pass (odd: see the bank note below)
+    constexpr int HW = 4 * T;   // columns of one half strip (4 runs)
+    constexpr int TX = 2 * HW;  // 248 output columns per strip
+    constexpr int NP = TX / 2;  // column pairs of the column pass (124 of the 128 threads)
+    constexpr int NT = 128;
 
-    // Smallest box width >= need that keeps 16-byte shared-memory loads of 8 consecutive rows
-    // conflict free (width = 4 mod 8 floats) and is a legal TMA box (multiple of 4 floats).
-    __host__ __device__ constexpr int box_width(int need)
+    // Smallest width >= need with width = 4 (mod 8) floats: a legal TMA box (multiple of 4
+    // floats) whose rows r = 0..7 start in eight different groups of four banks.
+    __host__ __device__ constexpr int pad_4mod8(int need)
     {
       int b = (need + 3) & ~3;
       while (b % 8 != 4)
@@ -69,28 +73,42 @@ namespace sb {
       return b;
     }
 
-    template <int K, int NW>
+    // Shared-memory bank note.  In the row pass a lane is (row r8 = lane & 7 of its warp's
+    // eight rows, run g = lane >> 3 of the row's four runs); at step i it reads word
+    // row * BW + skew + T g + i (+ the same in the second region).  With BW = 4 (mod 8) the
+    // eight rows fall into eight different groups of four banks, and with T odd the four
+    // runs take the four banks of a group: 32 lanes, 32 banks, for scalar 4-byte loads that
+    // land directly in the two halves of an f32x2 register pair (no packing moves).  The
+    // stores into F (pitch PF = 4 (mod 8)) are conflict free for the same reason.
+    // NBUF: staging buffers.  2 = TMA runs two blocks ahead, two CTAs per SM; 1 = the next block
+    // is requested as soon as the row pass has consumed the current one (it lands under the
+    // column pass), three CTAs per SM.
+    template <int K, int NBUF>
     struct MC
     {
       static constexpr int c = K / 2;
       static constexpr int skew = (4 - c % 4) % 4;  // TMA x coordinates must be 16-byte aligned
-      static constexpr int LEAD = c + skew;         // staged column of the region's first output column
-      static constexpr int TX = NW * WC;
-      static constexpr int NREG = (NW + 1) / 2;     // TMA regions (128 output columns each; 64 when NW == 1)
-      static constexpr int RW = NW >= 2 ? 128 : 64;
-      static constexpr int BW = box_width(RW + 2 * c + skew);
-      static constexpr int PF = TX + 1;             // odd pitch: lanes = rows store conflict free
+      static constexpr int LEAD = c + skew;         // staged column of a region's first output column
+      static constexpr int BW = pad_4mod8(HW + 2 * c + skew);
+      static constexpr int PF = pad_4mod8(TX);
       static constexpr int NIN = T + 2 * c;         // inputs of one run
-      static constexpr int NCH = (skew + NIN + 3) / 4;
       static constexpr int region_floats = R * BW;
-      static constexpr int raw_floats = NREG * region_floats;  // one buffer
-      static constexpr int off_F = 2 * raw_floats;
-      static constexpr int off_bar = off_F + ((R * PF + 3) & ~3);
+      static constexpr int raw_floats = 2 * region_floats;  // one buffer: two regions (half strips)
+      static constexpr int PER_SM = NBUF == 2 ? 2 : 3;
+      static constexpr int off_F = NBUF * raw_floats;
+      // G(s-1) for the DoG epilogue comes back from L2 through a cp.async ring in shared memory
+      // (8 bytes per thread and row); it takes whatever room two resident CTAs leave, and the
+      // prefetch distance is its depth minus one.
+      static constexpr int off_ring = off_F + R * PF;
+      static constexpr int budget_floats = (233472 / PER_SM - 1024 - 64) / 4;
+      static constexpr int RING = (budget_floats - off_ring) / (2 * NT) < 12 ? (budget_floats - off_ring) / (2 * NT) : 12;
+      static constexpr int PD = RING - 1;
+      static constexpr int off_bar = off_ring + RING * 2 * NT;
       static constexpr int smem_bytes = off_bar * 4 + 32;
+      static_assert(RING >= 5, "prefetch ring too short");
       static_assert(BW <= 256, "TMA box dimension limit");
-      static_assert(LEAD % 4 == 0, "aligned TMA coordinates");
-      static_assert((NW >= 2 ? 64 : 0) + 32 + 4 * NCH <= BW, "row-pass chunks stay inside the staged region");
-      static_assert(2 * c <= R - PD, "ramp-up fits the first block");
+      static_assert(LEAD % 4 == 0 && HW % 4 == 0, "aligned TMA coordinates");
+      static_assert(T % 2 == 1 && BW % 8 == 4 && PF % 8 == 4, "bank-conflict-free layout");
     };
 
     struct Params
@@ -106,11 +124,11 @@ namespace sb {
       float taps[16];    // the c + 1 distinct taps k[0 .. c]
     };
 
-    template <int K, int NW>
-    __global__ void __launch_bounds__(NW * 32, NW == 4 ? 2 : 4)
+    template <int K, int NBUF>
+    __global__ void __launch_bounds__(NT, NBUF == 2 ? 2 : 3)
         march_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Params prm)
     {
-      using S = MC<K, NW>;
+      using S = MC<K, NBUF>;
       constexpr int c = S::c, BW = S::BW, PF = S::PF, skew = S::skew;
       extern __shared__ __align__(1024) unsigned char smem_raw[];
       float* sm = reinterpret_cast<float*>(smem_raw);
@@ -119,13 +137,13 @@ namespace sb {
 
       const int tid = threadIdx.x, lane = tid & 31, wq = tid >> 5;
       const int w = prm.w, h = prm.h;
-      const int x0 = blockIdx.x * S::TX;
+      const int x0 = blockIdx.x * TX;
       const int y0 = blockIdx.y * prm.hy;
       const int y1 = min(y0 + prm.hy, h);
       const int r_begin = y0 - c, r_end = y1 + c;  // virtual rows fed to the column pass
       const int NB = (min(r_end, h) - 1 - r_begin) / R + 1;  // blocks that hold a real row
-      const int n_reg_on = (S::NREG == 2 && x0 + 128 >= w) ? 1 : S::NREG;
-      const bool edge = x0 == 0 || x0 + S::TX + c > w;  // some staged column lies outside the image
+      const int n_reg_on = x0 + HW >= w ? 1 : 2;
+      const bool edge = x0 == 0 || x0 + TX + c > w;  // some staged column lies outside the image
 
       if (tid == 0)
       {
@@ -137,58 +155,75 @@ namespace sb {
       __syncthreads();
 
       auto issue = [&](int u) {  // thread 0
-        void* bar = &bars[u & 1];
+        void* bar = &bars[u % NBUF];
         mbar_expect_tx(bar, static_cast<unsigned>(n_reg_on * S::region_floats * 4));
-        float* dst = sm + (u & 1) * S::raw_floats;
+        float* dst = sm + (u % NBUF) * S::raw_floats;
         for (int g = 0; g < n_reg_on; ++g)
-          tma_load_2d(dst + g * S::region_floats, &tmap, x0 - S::LEAD + 128 * g, r_begin + R * u, bar);
+          tma_load_2d(dst + g * S::region_floats, &tmap, x0 - S::LEAD + HW * g, r_begin + R * u, bar);
       };
       if (tid == 0)
       {
         issue(0);
-        if (NB > 1)
+        if (NBUF == 2 && NB > 1)
           issue(1);
       }
 
       const u64 one = pack2(prm.one, prm.one);
       const u64 neg_one = pack2(prm.neg_one, prm.neg_one);
-      const bool warp_on = x0 + WC * wq < w;  // warp-uniform: this warp's columns exist
 
-      // ---- column-pass state (lives across blocks) ----
-      const int fc = WC * wq + lane;         // F column of the low half; the high half is 32 further
-      const int xa = x0 + fc;                // image column of the low half
-      const bool lo_ok = xa < w, hi_ok = xa + 32 < w;
+      // ---- row-pass roles ----
+      const int r_row = 8 * wq + (lane & 7);  // row of the block
+      const int r_run = lane >> 3;            // run of the row (both halves)
+      const int r_in = r_row * BW + skew + T * r_run;  // first input word inside a region
+      float* const r_out = F + r_row * PF + T * r_run;
+
+      // ---- column-pass roles and state (lives across blocks) ----
+      const int xa = x0 + 2 * tid;  // image column of the low half; the high half is the next column
+      const bool col_on = tid < NP && xa < w;
+      const bool warp_on = x0 + 64 * wq < w && 32 * wq < NP;  // warp-uniform
       u64 A[2 * c];
 #pragma unroll
       for (int s = 0; s < 2 * c; ++s)
         A[s] = 0ull;
-      const float* gsrc = prm.src + xa;
-      auto load_prev = [&](int y) {  // G(s-1)(xa, y), G(s-1)(xa + 32, y); y clamped (unused when outside)
-        const size_t o = static_cast<size_t>(min(max(y, 0), h - 1)) * prm.src_pitch;
-        const float a = lo_ok ? __ldg(gsrc + o) : 0.f;
-        const float b = hi_ok ? __ldg(gsrc + o + 32) : 0.f;
-        return pack2(a, b);
+      const long long pitch_b = static_cast<long long>(prm.pitch) * 4;
+      const long long spitch_b = static_cast<long long>(prm.src_pitch) * 4;
+      const long long dog_delta = reinterpret_cast<const char*>(prm.dog) - reinterpret_cast<const char*>(prm.out);
+      // output pointer of the step about to run (output row y = r - c)
+      char* po = reinterpret_cast<char*>(prm.out) + (static_cast<long long>(r_begin - c) * prm.pitch + xa) * 4;
+      // G(s-1) prefetch: row yw goes to ring slot slot_w; the step about to run reads slot_r
+      constexpr int RING = S::RING, PD = S::PD;
+      u64* const ring = reinterpret_cast<u64*>(sm + S::off_ring) + tid;
+      const bool dog_on = col_on && prm.dog != nullptr;
+      const char* pgw =
+          reinterpret_cast<const char*>(prm.src) + (static_cast<long long>(r_begin - c) * prm.src_pitch + xa) * 4;
+      int yw = r_begin - c, slot_w = 0, slot_r = 0;
+      auto prefetch = [&]() {
+        if (dog_on && yw >= 0 && yw < h)
+          cp_async8(ring + slot_w * NT, pgw);
+        cp_async_commit();
+        pgw += spitch_b;
+        ++yw;
+        slot_w = slot_w + 1 == RING ? 0 : slot_w + 1;
       };
-      u64 gq[PD];
 #pragma unroll
       for (int q = 0; q < PD; ++q)
-        gq[q] = warp_on ? load_prev(r_begin - c + q) : 0ull;
+        prefetch();
 
       for (int u = 0; u < NB; ++u)
       {
-        float* raw = sm + (u & 1) * S::raw_floats;
-        mbar_wait(&bars[u & 1], (u >> 1) & 1);
+        float* raw = sm + (u % NBUF) * S::raw_floats;
+        mbar_wait(&bars[u % NBUF], (u / NBUF) & 1);
         const int rb = r_begin + R * u;  // first row of this block
 
         if (edge)  // CTA-uniform
         {
           // replicate the border pixel into the staged columns that lie outside the image
-          if (tid < S::NREG * R)
+          if (tid < 2 * R)
           {
             const int g = tid / R, row = tid - g * R;
             float* rr = raw + g * S::region_floats + row * BW;
-            const int xs = x0 - S::LEAD + 128 * g;  // image column of staged column 0
-            const int p0 = -xs;                     // staged column of image column 0
+            const int xs = x0 - S::LEAD + HW * g;  // image column of staged column 0
+            const int p0 = -xs;                    // staged column of image column 0
             if (xs < 0 && p0 < BW)
             {
               const float v = rr[p0];
@@ -208,25 +243,34 @@ namespace sb {
         }
 
         // ---------------- row pass: raw block -> F ----------------
-        if (warp_on)
+        // Inputs are consumed in groups of RG; a group's loads are issued one group ahead and
+        // a __syncwarp() closes every group.  The fence is a scheduling device: without it
+        // ptxas hoists all the loads of this straight-line code to the top and then, short of
+        // registers, re-orders the arithmetic output by output -- serial chains of dependent
+        // FFMA2 -- instead of input by input (2c + 1 independent FFMA2 per input).
         {
-          const float* rlo = raw + (wq >> 1) * S::region_floats + lane * BW + WC * (wq & 1);
-          float* fo = F + lane * PF + WC * wq;
+          const float* in0 = raw + r_in;
+          const float* in1 = in0 + S::region_floats;
+          constexpr int RG = 4, NG = (S::NIN + RG - 1) / RG;
           u64 acc[T];
+          u64 vin[NG * RG];
 #pragma unroll
-          for (int ch = 0; ch < S::NCH; ++ch)
+          for (int e = 0; e < RG; ++e)
+            vin[e] = pack2(in0[e], in1[e]);
+#pragma unroll
+          for (int g = 0; g < NG; ++g)
           {
-            const float4 a4 = *reinterpret_cast<const float4*>(rlo + 4 * ch);
-            const float4 b4 = *reinterpret_cast<const float4*>(rlo + 32 + 4 * ch);
-            const float av[4] = {a4.x, a4.y, a4.z, a4.w};
-            const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
+            for (int e = 0; e < RG; ++e)  // next group's inputs
+              if ((g + 1) * RG + e < S::NIN)
+                vin[(g + 1) * RG + e] = pack2(in0[(g + 1) * RG + e], in1[(g + 1) * RG + e]);
+#pragma unroll
+            for (int e = 0; e < RG; ++e)
             {
-              const int i = 4 * ch + e - skew;  // input index of the run: image column (run start) - c + i
-              if (i < 0 || i >= S::NIN)
+              const int i = g * RG + e;  // input i <-> image column (run start) - c + i
+              if (i >= S::NIN)
                 continue;
-              const u64 v = pack2_once(av[e], bv[e]);
+              const u64 v = vin[i];
               const int jlo = i - T + 1 > 0 ? i - T + 1 : 0;
               const int jhi = i < K - 1 ? i : K - 1;
               u64 p[c + 1];
@@ -247,92 +291,84 @@ namespace sb {
               if (i >= 2 * c)
               {
                 const int t = i - 2 * c;
-                fo[t] = lo2(acc[t]);
-                fo[t + 32] = hi2(acc[t]);
+                r_out[t] = lo2(acc[t]);
+                r_out[t + HW] = hi2(acc[t]);
               }
             }
+            __syncwarp();
           }
         }
         __syncthreads();  // F complete, raw buffer free
-        if (tid == 0 && u + 2 < NB)
+        if (tid == 0 && u + NBUF < NB)
         {
           if (edge)
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          issue(u + 2);
+          issue(u + NBUF);
         }
 
         // ---------------- column pass: F -> G(s), D(s-1), next octave ----------------
         if (warp_on)
         {
-          const int n_steps = u == NB - 1 ? ((r_end - rb + PD - 1) / PD) * PD : R;
-          for (int k0 = 0; k0 < n_steps; k0 += PD)
+          const int n_steps = u == NB - 1 ? r_end - rb : R;
+          // F row of step k: the block row of image row clamp(rb + k) (border rows replicate)
+          const int k_lo = max(-rb, 0), k_hi = min(h - 1 - rb, R - 1);
+          // steps whose output row y = rb + k - c lies in [y0, y1)
+          const int ks_lo = y0 + c - rb;
+          const float* fcol = F + 2 * tid;
+#pragma unroll 4
+          for (int k = 0; k < n_steps; ++k)
           {
+            prefetch();  // G(s-1) of the output row PD steps ahead
+            const int fr = min(max(k, k_lo), k_hi);
+            const u64 v = *reinterpret_cast<const u64*>(fcol + fr * PF);
+            u64 p[c + 1];
 #pragma unroll
-            for (int q = 0; q < PD; ++q)
-            {
-              const int r = rb + k0 + q;
-              const int fr = min(max(r, 0), h - 1) - rb;
-              const float* fp = F + fr * PF + fc;
-              const u64 v = pack2_once(fp[0], fp[32]);
-              u64 p[c + 1];
+            for (int m = 0; m <= c; ++m)
+              p[m] = mul2(v, pack2(prm.taps[m], prm.taps[m]));
+            const u64 E = add2(A[0], p[0], one);
 #pragma unroll
-              for (int m = 0; m <= c; ++m)
-                p[m] = mul2(v, pack2(prm.taps[m], prm.taps[m]));
-              const u64 E = add2(A[0], p[0], one);
-#pragma unroll
-              for (int s = 1; s < 2 * c; ++s)
-                A[s - 1] = add2(A[s], p[s <= c ? s : 2 * c - s], one);
-              A[2 * c - 1] = add2(0ull, p[0], one);
+            for (int s = 1; s < 2 * c; ++s)
+              A[s - 1] = add2(A[s], p[s <= c ? s : 2 * c - s], one);
+            A[2 * c - 1] = add2(0ull, p[0], one);
 
-              const int y = r - c;
-              if (y >= y0 && y < y1)
+            if (k >= ks_lo)  // uniform; k < ks_hi holds for every step of the loop
+            {
+              cp_async_wait<PD>();  // the copy issued PD steps ago (this row) has landed
+              if (col_on)
               {
-                const size_t o = static_cast<size_t>(y) * prm.pitch + xa;
-                if (lo_ok)
-                  prm.out[o] = lo2(E);
-                if (hi_ok)
-                  prm.out[o + 32] = hi2(E);
+                // 8-byte stores: when w is odd the high half of the last pair falls into the row padding
+                *reinterpret_cast<u64*>(po) = E;
                 if (prm.dog != nullptr)
+                  *reinterpret_cast<u64*>(po + dog_delta) = add2(ring[slot_r * NT], E, neg_one);  // RN(E - G(s-1))
+                const int y = rb + k - c;
+                if (prm.nextG != nullptr && (y & 1) == 0)
                 {
-                  const u64 d = add2(gq[q], E, neg_one);  // RN(E - G(s-1)): gq * (-1) + E
-                  if (lo_ok)
-                    prm.dog[o] = lo2(d);
-                  if (hi_ok)
-                    prm.dog[o + 32] = hi2(d);
-                }
-                if (prm.nextG != nullptr && ((y | lane) & 1) == 0)
-                {
-                  // downscale(G(s), 2): even rows and columns (xa is even when the lane is)
+                  // downscale(G(s), 2): even rows and columns (xa is even)
                   const int yy = y >> 1, xx = xa >> 1;
-                  if (yy < prm.nh)
-                  {
-                    float* pn = prm.nextG + static_cast<size_t>(yy) * prm.npitch;
-                    if (lo_ok && xx < prm.nw)
-                      pn[xx] = lo2(E);
-                    if (hi_ok && xx + 16 < prm.nw)
-                      pn[xx + 16] = hi2(E);
-                  }
+                  if (yy < prm.nh && xx < prm.nw)
+                    prm.nextG[static_cast<size_t>(yy) * prm.npitch + xx] = lo2(E);
                 }
               }
-              gq[q] = load_prev(y + PD);
             }
+            po += pitch_b;
+            slot_r = slot_r + 1 == RING ? 0 : slot_r + 1;
           }
         }
         __syncthreads();  // F free
       }
     }
 
-    template <int K, int NW>
+    template <int K, int NBUF>
     bool launch(const float* src, int src_pitch, float* dst, float* dog, float* nextG, int w, int h, int pitch, int nw,
                 int nh, int npitch, const Taps& taps, cudaStream_t st)
     {
-      using S = MC<K, NW>;
-      constexpr int per_sm = NW == 4 ? 2 : 4;
+      using S = MC<K, NBUF>;
+      constexpr int per_sm = S::PER_SM;
       static_assert(per_sm * (S::smem_bytes + 1024) <= 233472, "resident CTAs must fit one SM");
       static bool configured = false;
       if (!configured)
       {
-        if (cudaFuncSetAttribute(march_kernel<K, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::smem_bytes) !=
+        if (cudaFuncSetAttribute(march_kernel<K, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::smem_bytes) !=
             cudaSuccess)
           return false;
         configured = true;
@@ -368,7 +404,7 @@ namespace sb {
 
       // Segments: fill the machine (148 SMs x resident CTAs) while keeping segments tall --
       // every segment pays 2c warm-up rows and whole 32-row blocks in the row pass.
-      const int n_strips = (w + S::TX - 1) / S::TX;
+      const int n_strips = (w + TX - 1) / TX;
       const int slots = 148 * per_sm;
       int best_segs = 1;
       double best_cost = 1e30;
@@ -379,7 +415,7 @@ namespace sb {
         if ((h + hy - 1) / hy != n)
           continue;
         const int blocks = (hy + 2 * S::c + R - 1) / R;
-        const double cta = blocks * R * 1.15 + (hy + 2 * S::c);      // row pass (T = 32 ramps) + column pass
+        const double cta = blocks * R * 1.15 + (hy + 2 * S::c);      // row pass (ramps of the runs) + column pass
         const int ctas = n_strips * n;
         const int per = (ctas + 147) / 148;                            // CTAs on the busiest SM
         // one CTA alone on an SM leaves its barrier bubbles uncovered
@@ -398,7 +434,7 @@ namespace sb {
       int hy = (h + n_segs - 1) / n_segs;
       n_segs = (h + hy - 1) / hy;
       prm.hy = hy;
-      march_kernel<K, NW><<<dim3(n_strips, n_segs), NW * 32, S::smem_bytes, st>>>(tmap, prm);
+      march_kernel<K, NBUF><<<dim3(n_strips, n_segs), NT, S::smem_bytes, st>>>(tmap, prm);
       return true;
     }
 
@@ -406,11 +442,13 @@ namespace sb {
     bool launch_k(const float* src, int src_pitch, float* dst, float* dog, float* nextG, int w, int h, int pitch,
                   int nw, int nh, int npitch, const Taps& taps, cudaStream_t st)
     {
-      if (w > 640)
-        return launch<K, 4>(src, src_pitch, dst, dog, nextG, w, h, pitch, nw, nh, npitch, taps, st);
-      if (w > 64)
-        return launch<K, 2>(src, src_pitch, dst, dog, nextG, w, h, pitch, nw, nh, npitch, taps, st);
-      return launch<K, 1>(src, src_pitch, dst, dog, nextG, w, h, pitch, nw, nh, npitch, taps, st);
+      static const int nbuf = [] {
+        const char* e = getenv("SARA_B200_MARCH_NBUF");
+        return e ? atoi(e) : 2;
+      }();
+      if (nbuf == 1)
+        return launch<K, 1>(src, src_pitch, dst, dog, nextG, w, h, pitch, nw, nh, npitch, taps, st);
+      return launch<K, 2>(src, src_pitch, dst, dog, nextG, w, h, pitch, nw, nh, npitch, taps, st);
     }
 
   }  // namespace march

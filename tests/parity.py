@@ -74,8 +74,35 @@ def match_oriented(k_gpu: np.ndarray, k_ref: np.ndarray):
     return np.asarray(ig, int)[order], np.asarray(ir, int)[order], bad, len(set(dr) | set(dg))
 
 
-def compare_keypoints(k_gpu, d_gpu, k_ref, d_ref, scaling=None):
-    """Returns a dict of statistics and asserts the tolerances above."""
+def explain_descriptor_outliers(ref, k_gpu_oct, d_gpu, idx_gpu):
+    """Descriptors outside the tolerance must be explained by the reference's own
+    discontinuity: accumulate() truncates with modf (quirk N6), so a sample a hair inside
+    `pos > -1` carries a weight near 2 instead of 0, and whether it is inside depends on the
+    last bits of the keypoint orientation.  The GPU's orientation differs from the oracle's by
+    ~1e-6 rad (atan2f / expf of CUDA vs glibc); feeding the GPU's orientation to the ORACLE's
+    ComputeSIFTDescriptor (FeatureDescriptors/SIFT.hpp:62-145) must reproduce the GPU descriptor
+    within the tolerance.  Returns the indices that are NOT explained."""
+    from oracle import oracle as O
+
+    grads, unexplained = {}, []
+    for i in idx_gpu:
+        kp = k_gpu_oct[i]
+        key = (int(kp["s"]), int(kp["o"]))
+        if key not in grads:
+            grads[key] = O.gradient_polar(ref.gaussian(*key))
+        sigma = float(np.float32(1.0) / np.sqrt(np.float32(kp["shape"][0])))
+        d = O.sift_descriptor(grads[key], float(kp["x"]), float(kp["y"]), sigma, float(kp["orientation"]))
+        err = np.linalg.norm(d.astype(np.float64) - d_gpu[i].astype(np.float64))
+        if not err <= DESC_REL * np.linalg.norm(d.astype(np.float64)) + DESC_ABS:
+            unexplained.append(int(i))
+    return unexplained
+
+
+def compare_keypoints(k_gpu, d_gpu, k_ref, d_ref, ref=None, k_gpu_oct=None):
+    """Returns a dict of statistics and asserts the tolerances above.  With `ref` (the oracle
+    result) and `k_gpu_oct` (the GPU's oriented keypoints in octave coordinates) every
+    descriptor outside the tolerance must additionally be EXPLAINED (see
+    explain_descriptor_outliers); without them only the fraction is checked."""
     ig, ir, bad, n_ext = match_oriented(k_gpu, k_ref)
     stats = {"n_gpu": len(k_gpu), "n_ref": len(k_ref), "extrema": n_ext, "count_mismatch": bad}
     if n_ext:
@@ -100,5 +127,14 @@ def compare_keypoints(k_gpu, d_gpu, k_ref, d_ref, scaling=None):
     stats["desc_err_max"] = float(err.max())
     stats["desc_err_median"] = float(np.median(err))
     stats["desc_bad"] = int((~ok_desc).sum())
-    assert ok_desc.mean() >= DESC_FRACTION, f"{(~ok_desc).sum()}/{len(ok_desc)} descriptors beyond tolerance (max {err.max()})"
+    n_bad = int((~ok_desc).sum())
+    if ref is not None and k_gpu_oct is not None and n_bad:
+        assert len(k_gpu_oct) == len(k_gpu)
+        unexplained = explain_descriptor_outliers(ref, k_gpu_oct, d_gpu, ig[~ok_desc])
+        stats["desc_bad_unexplained"] = len(unexplained)
+        assert not unexplained, f"descriptors {unexplained} differ and the GPU orientation does not explain it"
+        assert n_bad <= max(2, int(5 * (1 - DESC_FRACTION) * len(ok_desc))), f"{n_bad}/{len(ok_desc)} descriptors beyond tolerance"
+    else:
+        assert n_bad <= max(1, int((1 - DESC_FRACTION) * len(ok_desc))), \
+            f"{n_bad}/{len(ok_desc)} descriptors beyond tolerance (max {err.max()})"
     return stats

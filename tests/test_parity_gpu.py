@@ -175,7 +175,7 @@ def test_sift_keypoints(ctx, w, h, fo, seed):
     assert_pyramids_identical(ctx, ref)
     assert_extrema_identical(ctx.extrema(), ref.extrema)
     assert len(ref.keypoints) > 50
-    stats = compare_keypoints(kl.features, kl.descriptors, ref.keypoints, ref.descriptors)
+    stats = compare_keypoints(kl.features, kl.descriptors, ref.keypoints, ref.descriptors, ref, ctx.oriented())
     print(stats)
     # octave-coordinate list (before SIFT.cpp:92-98) matches too
     ko = ctx.oriented()
@@ -254,7 +254,7 @@ def test_sift_other_parameters(ctx, kw, args):
     assert_pyramids_identical(ctx, ref)
     assert_extrema_identical(ctx.extrema(), ref.extrema)
     assert len(ref.keypoints) > 20
-    compare_keypoints(kl.features, kl.descriptors, ref.keypoints, ref.descriptors)
+    compare_keypoints(kl.features, kl.descriptors, ref.keypoints, ref.descriptors, ref, ctx.oriented())
 
 
 @pytest.mark.parametrize("fo,s0", [(0, 1.0), (-1, 1.0), (0, 0.8), (-1, 1.6)])
@@ -298,7 +298,7 @@ def test_c4_sequence_frames_vs_oracle(i):
         assert_pyramids_identical(c, ref)
         assert_extrema_identical(c.extrema(), ref.extrema)
         assert len(ref.keypoints) > 1000
-        print(compare_keypoints(kl.features, kl.descriptors, ref.keypoints, ref.descriptors))
+        print(compare_keypoints(kl.features, kl.descriptors, ref.keypoints, ref.descriptors, ref, c.oriented()))
     finally:
         c.close()
 
@@ -314,7 +314,7 @@ def test_sift_ragged_shapes(ctx, w, h):
         assert_pyramids_identical(c, ref)
         assert_extrema_identical(c.extrema(), ref.extrema)
         if len(ref.keypoints):
-            compare_keypoints(kl.features, kl.descriptors, ref.keypoints, ref.descriptors)
+            compare_keypoints(kl.features, kl.descriptors, ref.keypoints, ref.descriptors, ref, c.oriented())
     finally:
         c.close()
 

@@ -46,7 +46,7 @@ def test_c3_4k_full_sift_vs_oracle(ctx4k):
     assert_pyramids_identical(ctx4k, ref)
     assert_extrema_identical(ctx4k.extrema(), ref.extrema)
     assert len(ref.keypoints) > 5000
-    stats = compare_keypoints(kl.features, kl.descriptors, ref.keypoints, ref.descriptors)
+    stats = compare_keypoints(kl.features, kl.descriptors, ref.keypoints, ref.descriptors, ref, ctx4k.oriented())
     print(stats)
 
 
