@@ -159,6 +159,11 @@ SARA_B200_API int sara_b200_set_pyramid_mode(sara_b200_ctx* ctx, int mode);
  * on side streams.  Turning this off serialises them (used to time single launches alone). */
 SARA_B200_API int sara_b200_set_octave_overlap(sara_b200_ctx* ctx, int on);
 
+/* sara_b200_sift_enqueue[_u8] replays a CUDA graph of the frame's launch sequence (captured
+ * the first time a geometry / argument set / device pointer is seen on a slot; on by
+ * default, off while profiling).  Turning it off issues every launch directly. */
+SARA_B200_API int sara_b200_set_graphs(sara_b200_ctx* ctx, int on);
+
 /* Record CUDA events around the stages (sara_b200_last_timings). */
 SARA_B200_API int sara_b200_set_profiling(sara_b200_ctx* ctx, int on);
 SARA_B200_API int sara_b200_last_timings(sara_b200_ctx* ctx, int slot, sara_b200_timings* out);
@@ -203,6 +208,11 @@ SARA_B200_API int sara_b200_sift_enqueue(sara_b200_ctx* ctx, int slot, const flo
  * skip that copy), frees the slot. */
 SARA_B200_API int sara_b200_collect(sara_b200_ctx* ctx, int slot, sara_b200_keypoint* keypoints,
                       float* descriptors, int capacity, int* n_out);
+/* Same as sara_b200_collect, but into caller-owned DEVICE buffers (device-to-device copies):
+ * for consumers that stay on the GPU -- a matcher, or the NCCL gather of a multi-GPU run
+ * (sara_b200/parallel.py).  Frees the slot. */
+SARA_B200_API int sara_b200_collect_device(sara_b200_ctx* ctx, int slot, sara_b200_keypoint* d_keypoints,
+                             float* d_descriptors, int capacity, int* n_out);
 /* Device-resident results of a finished slot (for GPU consumers such as a
  * matcher): pointers stay valid until the slot is enqueued again. */
 SARA_B200_API int sara_b200_device_results(sara_b200_ctx* ctx, int slot, const sara_b200_keypoint** keypoints,

@@ -24,6 +24,7 @@
 // ========================================================================== //
 #pragma once
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <limits>
@@ -257,9 +258,17 @@ namespace sara_b200 {
   // host thread keeps that contract, see the threading note in sara_b200.h).
   inline Context& default_context(int w, int h)
   {
+    // Sized for the largest width and the largest height seen so far, so that frames of
+    // alternating orientation do not recreate it on every call.
     thread_local std::unique_ptr<Context> ctx;
+    thread_local int max_w = 0, max_h = 0;
     if (!ctx || !ctx->fits(w, h))
-      ctx = std::make_unique<Context>(w, h);
+    {
+      max_w = std::max(max_w, w);
+      max_h = std::max(max_h, h);
+      ctx.reset();
+      ctx = std::make_unique<Context>(max_w, max_h);
+    }
     return *ctx;
   }
 

@@ -19,3 +19,4 @@ from .api import (  # noqa: F401
     library_path,
     load_library,
 )
+from .features_io import read_keypoints, remove_redundant_features, write_keypoints  # noqa: F401,E402

@@ -90,6 +90,7 @@ SYMBOLS = [
     "sara_b200_layer_size", "sara_b200_octave_scaling_factor", "sara_b200_copy_layer",
     "sara_b200_copy_extrema", "sara_b200_copy_oriented", "sara_b200_gaussian",
     "sara_b200_make_gaussian_kernel", "sara_b200_sift_u8", "sara_b200_sift_enqueue_u8", "sara_b200_to_gray32f",
+    "sara_b200_collect_device", "sara_b200_set_graphs",
 ]
 
 
@@ -122,6 +123,7 @@ def load_library() -> C.CDLL:
     L.sara_b200_set_profiling.argtypes = [vp, C.c_int]
     L.sara_b200_set_pyramid_mode.argtypes = [vp, C.c_int]
     L.sara_b200_set_octave_overlap.argtypes = [vp, C.c_int]
+    L.sara_b200_set_graphs.argtypes = [vp, C.c_int]
     L.sara_b200_last_timings.argtypes = [vp, C.c_int, C.POINTER(Timings)]
     L.sara_b200_sift.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(_SiftArgs), vp, vp, C.c_int, ip]
     L.sara_b200_sift_enqueue.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.POINTER(_SiftArgs), vp]
@@ -129,6 +131,7 @@ def load_library() -> C.CDLL:
     L.sara_b200_sift_enqueue_u8.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_SiftArgs), vp]
     L.sara_b200_to_gray32f.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp]
     L.sara_b200_collect.argtypes = [vp, C.c_int, vp, vp, C.c_int, ip]
+    L.sara_b200_collect_device.argtypes = [vp, C.c_int, vp, vp, C.c_int, ip]
     L.sara_b200_device_results.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), ip]
     L.sara_b200_wait.argtypes = [vp, C.c_int, ip]
     L.sara_b200_dog_extrema.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.POINTER(_DogArgs)]
@@ -274,6 +277,9 @@ class SiftContext:
     def set_octave_overlap(self, on: bool):
         self._check(self._L.sara_b200_set_octave_overlap(self._ctx, int(on)))
 
+    def set_graphs(self, on: bool):
+        self._check(self._L.sara_b200_set_graphs(self._ctx, int(on)))
+
     def set_profiling(self, on: bool):
         self._check(self._L.sara_b200_set_profiling(self._ctx, int(on)))
 
@@ -339,6 +345,21 @@ class SiftContext:
         self._check(self._L.sara_b200_collect(self._ctx, slot, kps.ctypes.data, desc.ctypes.data,
                                               len(kps), C.byref(m)))
         return KeypointList(kps[: m.value], desc[: m.value])
+
+    def collect_device(self, slot=0):
+        """Results of the slot as CUDA tensors (keypoints: (n, 52) uint8 records of KEYPOINT_DTYPE,
+        descriptors: (n, 128) float32), copied device to device; nothing crosses PCIe."""
+        import torch
+
+        n = self.wait(slot)
+        self._keep.pop(slot, None)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        kps = torch.empty((max(n, 1), 52), dtype=torch.uint8, device=dev)
+        desc = torch.empty((max(n, 1), 128), dtype=torch.float32, device=dev)
+        m = C.c_int()
+        self._check(self._L.sara_b200_collect_device(self._ctx, slot, kps.data_ptr(), desc.data_ptr(), max(n, 1),
+                                                     C.byref(m)))
+        return kps[: m.value], desc[: m.value]
 
     def collect_into(self, slot, kps_ptr, desc_ptr, capacity) -> int:
         m = C.c_int()

@@ -67,6 +67,24 @@ namespace {
     double top_kernel_bytes = 0.;
     sara_b200_timings timings{};
     int pyramid_launches = 0, total_launches = 0, extra_launches = 0, extra_launches_pre = 0;
+    // CUDA graphs of whole frames, keyed by everything the launch sequence depends on
+    // (geometry, arguments, input kind and -- for device-resident input -- the pointer).
+    struct FrameGraph
+    {
+      int w = 0, h = 0, u8_channels = 0, mode = 0;
+      bool on_device = false, overlap = true;
+      const void* dev_ptr = nullptr;
+      sara_b200_sift_args args{};
+      cudaGraphExec_t exec = nullptr;
+      PyramidDesc P{};
+      int n_segments = 0, downscale_index = 0, pyramid_launches = 0, total_launches = 0;
+      float *d_img = nullptr, *d_tmp = nullptr;
+      uint8_t* d_u8 = nullptr;
+      int* seg_offsets = nullptr;
+      unsigned long long last_use = 0;
+    };
+    std::vector<FrameGraph> graphs;
+    unsigned long long graph_clock = 0;
   };
 
   }  // namespace
@@ -79,6 +97,7 @@ struct sara_b200_ctx
   bool profiling = false;
   int pyramid_mode = SARA_B200_PYRAMID_AUTO;
   bool octave_overlap = true;
+  bool use_graphs = true;
   std::vector<Slot> slots;
   double* d_gray_lut = nullptr;   // 3 x 256 products of the rgb -> gray conversion (ingest.cu)
   float* scratch = nullptr;       // sara_b200_gaussian / sara_b200_to_gray32f work buffers (grown on demand)
@@ -262,6 +281,10 @@ namespace {
       if (S.arena)
       {
         CU(ctx, cudaStreamSynchronize(S.stream ? S.stream : S.own_stream));
+        for (auto& fg : S.graphs)  // they point into the old arena
+          if (fg.exec)
+            cudaGraphExecDestroy(fg.exec);
+        S.graphs.clear();
         CU(ctx, cudaFree(S.arena));
         S.arena = nullptr;
         S.arena_bytes = 0;
@@ -354,7 +377,7 @@ namespace {
   // which is converted on the device first (ingest.cu).
   int enqueue_pyramid(sara_b200_ctx* ctx, Slot& S, const void* image_any, int w, int h, bool on_device,
                       const sara_b200_pyramid_params& pp, float gauss_truncate, cudaStream_t st,
-                      const ExtremaParams* early = nullptr, int u8_channels = 0)
+                      const ExtremaParams* early = nullptr, int u8_channels = 0, bool skip_upload = false)
   {
     const float* image = static_cast<const float*>(image_any);
     Geometry g;
@@ -380,7 +403,8 @@ namespace {
       const uint8_t* d_u8 = static_cast<const uint8_t*>(image_any);
       if (!on_device)
       {
-        CU(ctx, cudaMemcpyAsync(S.d_u8, image_any, u8_bytes, cudaMemcpyHostToDevice, st));
+        if (!skip_upload)
+          CU(ctx, cudaMemcpyAsync(S.d_u8, image_any, u8_bytes, cudaMemcpyHostToDevice, st));
         d_u8 = S.d_u8;
       }
       if (u8_channels == 3)
@@ -392,7 +416,8 @@ namespace {
     }
     else if (!on_device)
     {
-      CU(ctx, cudaMemcpyAsync(S.d_img, image, sizeof(float) * w * h, cudaMemcpyHostToDevice, st));
+      if (!skip_upload)
+        CU(ctx, cudaMemcpyAsync(S.d_img, image, sizeof(float) * w * h, cudaMemcpyHostToDevice, st));
       d_src = S.d_img;
     }
     if (prof)
@@ -856,6 +881,9 @@ void sara_b200_destroy(sara_b200_ctx* ctx)
       cudaStreamSynchronize(S.own_stream);
     if (S.stream && S.stream != S.own_stream && S.busy)
       cudaStreamSynchronize(S.stream);
+    for (auto& fg : S.graphs)
+      if (fg.exec)
+        cudaGraphExecDestroy(fg.exec);
     cudaFree(S.arena);
     cudaFree(S.kbuf);
     cudaFreeHost(S.h_counters);
@@ -925,6 +953,14 @@ int sara_b200_set_octave_overlap(sara_b200_ctx* ctx, int on)
   return 0;
 }
 
+int sara_b200_set_graphs(sara_b200_ctx* ctx, int on)
+{
+  if (!ctx)
+    return SARA_B200_ERR_BAD_ARG;
+  ctx->use_graphs = on != 0;
+  return 0;
+}
+
 int sara_b200_last_timings(sara_b200_ctx* ctx, int slot, sara_b200_timings* out)
 {
   int rc = check_slot(ctx, slot);
@@ -962,21 +998,131 @@ static int sift_enqueue_impl(sara_b200_ctx* ctx, int slot, const void* image, in
     return fail(ctx, SARA_B200_ERR_BAD_ARG,
                 "img_padding_sz must be >= 1 (the 3x3x3 neighbourhood must stay inside the layer)");
   const ExtremaParams early{args->extremum_thres, args->edge_ratio_thres, args->extremum_refinement_iter, 5};
-  rc = enqueue_pyramid(ctx, S, image, w, h, image_on_device != 0, args->pyramid_params, args->gauss_truncate, st,
-                       &early, u8_channels);
-  if (rc)
-    return rc;
-  // Quirk N1 (SIFT.cpp:45-51 vs DoG.hpp:72-78): extremum_refinement_iter lands in
-  // the img_padding_sz slot; the iteration count keeps its default, 5.
-  rc = enqueue_extrema(ctx, S, args->extremum_thres, args->edge_ratio_thres,
-                       args->extremum_refinement_iter, 5, st);
-  if (rc)
-    return rc;
-  rc = enqueue_describe(ctx, S, st);
-  if (rc)
-    return rc;
+  const bool on_device = image_on_device != 0;
+  // Records the frame's whole launch sequence on `st` (everything but the host -> device copy
+  // when `skip_upload`).  Quirk N1 (SIFT.cpp:45-51 vs DoG.hpp:72-78): extremum_refinement_iter
+  // lands in the img_padding_sz slot; the iteration count keeps its default, 5.
+  auto record = [&](bool skip_upload) -> int {
+    int r = enqueue_pyramid(ctx, S, image, w, h, on_device, args->pyramid_params, args->gauss_truncate, st, &early,
+                            u8_channels, skip_upload);
+    if (r)
+      return r;
+    r = enqueue_extrema(ctx, S, args->extremum_thres, args->edge_ratio_thres, args->extremum_refinement_iter, 5, st);
+    if (r)
+      return r;
+    r = enqueue_describe(ctx, S, st);
+    if (r)
+      return r;
+    S.has_keypoints = true;
+    return finish_enqueue(ctx, S, st);
+  };
+  if (!ctx->use_graphs || ctx->profiling)
+    return record(false);
+
+  // ---- CUDA-graph path: one graph launch per frame instead of ~45 kernel launches, side-stream
+  // events and tensor-map encodes (the sequence is captured once per geometry / argument set) ----
+  Slot::FrameGraph* fg = nullptr;
+  for (auto& g : S.graphs)
+    if (g.w == w && g.h == h && g.u8_channels == u8_channels && g.on_device == on_device &&
+        g.mode == ctx->pyramid_mode && g.overlap == ctx->octave_overlap && (!on_device || g.dev_ptr == image) &&
+        std::memcmp(&g.args, args, sizeof(*args)) == 0)
+    {
+      fg = &g;
+      break;
+    }
+  if (!fg)
+  {
+    // size the arena outside the capture (layout_slot may allocate)
+    Geometry geo;
+    rc = plan_geometry(ctx, w, h, args->pyramid_params, &geo);
+    if (rc)
+      return rc;
+    rc = layout_slot(ctx, S, w, h, geo, args->pyramid_params, !on_device || u8_channels > 0,
+                     on_device ? 0 : static_cast<size_t>(w) * h * u8_channels);
+    if (rc)
+      return rc;
+    if (S.graphs.size() >= 8)  // evict the least recently used
+    {
+      auto lru = std::min_element(S.graphs.begin(), S.graphs.end(),
+                                  [](const Slot::FrameGraph& a, const Slot::FrameGraph& b) { return a.last_use < b.last_use; });
+      cudaGraphExecDestroy(lru->exec);
+      S.graphs.erase(lru);
+    }
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) != cudaSuccess)
+    {
+      cudaGetLastError();
+      ctx->use_graphs = false;
+      return record(false);
+    }
+    rc = record(true);
+    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    S.busy = false;
+    if (rc != 0 || ce != cudaSuccess || graph == nullptr)
+    {
+      if (graph)
+        cudaGraphDestroy(graph);
+      cudaGetLastError();
+      if (rc)
+        return rc;  // a genuine argument error: the direct path would fail the same way
+      ctx->use_graphs = false;
+      return record(false);
+    }
+    Slot::FrameGraph g;
+    const cudaError_t ie = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess)
+    {
+      cudaGetLastError();
+      ctx->use_graphs = false;
+      return record(false);
+    }
+    g.w = w;
+    g.h = h;
+    g.u8_channels = u8_channels;
+    g.mode = ctx->pyramid_mode;
+    g.on_device = on_device;
+    g.overlap = ctx->octave_overlap;
+    g.dev_ptr = on_device ? image : nullptr;
+    g.args = *args;
+    g.P = S.P;
+    g.n_segments = S.n_segments;
+    g.downscale_index = S.downscale_index;
+    g.pyramid_launches = S.pyramid_launches;
+    g.total_launches = S.total_launches;
+    g.d_img = S.d_img;
+    g.d_tmp = S.d_tmp;
+    g.d_u8 = S.d_u8;
+    g.seg_offsets = S.seg_offsets;
+    S.graphs.push_back(g);
+    fg = &S.graphs.back();
+  }
+  // restore the slot state the accessors read (another geometry may have run in between)
+  S.P = fg->P;
+  S.n_segments = fg->n_segments;
+  S.downscale_index = fg->downscale_index;
+  S.pyramid_launches = fg->pyramid_launches;
+  S.total_launches = fg->total_launches;
+  S.d_img = fg->d_img;
+  S.d_tmp = fg->d_tmp;
+  S.d_u8 = fg->d_u8;
+  S.seg_offsets = fg->seg_offsets;
+  S.img_w = w;
+  S.img_h = h;
+  S.stream = st;
+  S.classified_upto = 0;
+  fg->last_use = ++S.graph_clock;
+  if (!on_device)
+  {
+    if (u8_channels > 0)
+      CU(ctx, cudaMemcpyAsync(S.d_u8, image, static_cast<size_t>(w) * h * u8_channels, cudaMemcpyHostToDevice, st));
+    else
+      CU(ctx, cudaMemcpyAsync(S.d_img, image, sizeof(float) * w * h, cudaMemcpyHostToDevice, st));
+  }
+  CU(ctx, cudaGraphLaunch(fg->exec, st));
   S.has_keypoints = true;
-  return finish_enqueue(ctx, S, st);
+  S.busy = true;
+  return 0;
 }
 
 int sara_b200_sift_enqueue(sara_b200_ctx* ctx, int slot, const float* image, int w, int h,
@@ -1039,6 +1185,37 @@ int sara_b200_collect(sara_b200_ctx* ctx, int slot, sara_b200_keypoint* keypoint
       CU(ctx, cudaMemcpyAsync(keypoints, S.kp_out, sizeof(Keypoint) * c.n_kp, cudaMemcpyDeviceToHost, st));
     if (descriptors)
       CU(ctx, cudaMemcpyAsync(descriptors, S.desc, sizeof(float) * 128 * c.n_kp, cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+  }
+  return 0;
+}
+
+int sara_b200_collect_device(sara_b200_ctx* ctx, int slot, sara_b200_keypoint* d_keypoints, float* d_descriptors,
+                             int capacity, int* n_out)
+{
+  int rc = check_slot(ctx, slot);
+  if (rc)
+    return rc;
+  Slot& S = ctx->slots[slot];
+  rc = wait_slot(ctx, S);
+  if (rc)
+    return rc;
+  const Counters c = *S.h_counters;
+  if (n_out)
+    *n_out = c.n_kp;
+  if (c.overflow)
+    return fail(ctx, SARA_B200_ERR_OVERFLOW,
+                "frame exceeds the context capacity (candidates %d, extrema %d, keypoints %d; max_keypoints %d)",
+                c.n_cand, c.n_ext, c.n_kp, ctx->cap_kp);
+  if (c.n_kp > capacity)
+    return fail(ctx, SARA_B200_ERR_OVERFLOW, "%d keypoints exceed the caller's capacity %d", c.n_kp, capacity);
+  cudaStream_t st = S.stream ? S.stream : S.own_stream;
+  if (c.n_kp > 0)
+  {
+    if (d_keypoints)
+      CU(ctx, cudaMemcpyAsync(d_keypoints, S.kp_out, sizeof(Keypoint) * c.n_kp, cudaMemcpyDeviceToDevice, st));
+    if (d_descriptors)
+      CU(ctx, cudaMemcpyAsync(d_descriptors, S.desc, sizeof(float) * 128 * c.n_kp, cudaMemcpyDeviceToDevice, st));
     CU(ctx, cudaStreamSynchronize(st));
   }
   return 0;

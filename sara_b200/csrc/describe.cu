@@ -209,6 +209,11 @@ namespace sb {
 
     constexpr int DESC_WARPS = 4;
     constexpr int DESC_NC = 16;  // copies of the 128-bin histogram per warp; 32 / DESC_NC update phases
+    // 128 real bins + 8 scratch bins, one per contribution of a sample: a contribution whose
+    // "+1" spatial neighbour does not exist (xi == 3 or yi == 3) goes to ITS scratch bin, so the
+    // eight addresses of a sample are always distinct and its eight loads can be issued together
+    // (one shared-memory latency per update instead of eight dependent ones).
+    constexpr int DESC_BINS = 128 + 8;
 
     // atan2 for the descriptor's soft orientation binning: odd minimax polynomial on [0, 1]
     // (|error| < 1e-5 rad, i.e. 1.3e-5 of a bin; the binning is continuous in the angle, so this
@@ -249,10 +254,10 @@ namespace sb {
                           Counters* __restrict__ counters, int cap_kp, Keypoint* __restrict__ kp_out,
                           float* __restrict__ desc)
     {
-      extern __shared__ float s_dyn[];  // DESC_WARPS x (128 bins x 16 copies + 128 queue entries)
+      extern __shared__ float s_dyn[];  // DESC_WARPS x ((128 + 8) bins x 16 copies + 128 queue entries)
       const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-      float* priv = s_dyn + wid * (128 * DESC_NC + 128);
-      int* queue = reinterpret_cast<int*>(priv + 128 * DESC_NC);
+      float* priv = s_dyn + wid * (DESC_BINS * DESC_NC + 128);
+      int* queue = reinterpret_cast<int*>(priv + DESC_BINS * DESC_NC);
       const int lcopy = lane & (DESC_NC - 1);
       const int lphase = lane / DESC_NC;
       const int n = min(counters->n_kp, cap_kp);
@@ -287,8 +292,8 @@ namespace sb {
 
         // Histogram: DESC_NC copies of the 128 bins; the lanes that share a copy update it in
         // separate phases (fixed order => deterministic sums, no bank conflicts).
-#pragma unroll 8
-        for (int b = 0; b < 4 * DESC_NC; ++b)
+#pragma unroll 4
+        for (int b = 0; b < DESC_BINS * DESC_NC / 32; ++b)
           priv[b * 32 + lane] = 0.f;
 
         // A kept sample in two steps, so that the loads of several samples are in flight
@@ -333,12 +338,12 @@ namespace sb {
           }
           return sm;
         };
-        // What one kept sample adds to the histogram: 8 (address, value) pairs.  A missing
-        // +1 neighbour (xi == 3 or yi == 3) aliases the cell itself with a zero value, so the
-        // update is branch-free (x + 0 == x).
+        // What one kept sample adds to the histogram: 8 (address, value) pairs with DISTINCT
+        // addresses (a missing +1 neighbour -- xi == 3 or yi == 3 -- is redirected to the
+        // contribution's own scratch bin).
         struct Weights
         {
-          int p0, p1, dx, dy;  // float offsets into the lane's histogram copy
+          int a[8];  // float offsets into the lane's histogram copy
           float v[8];
         };
         auto weights = [&](const Sample& sm) {
@@ -364,14 +369,19 @@ namespace sb {
           const float wy0 = __fsub_rn(1.f, yfrac), wx0 = __fsub_rn(1.f, xfrac);
           const bool x1 = xi < 3, y1 = yi < 3;
           const int cell = ((4 * yi + xi) * 8) * DESC_NC + lcopy;
-          w.p0 = cell + (oi & 7) * DESC_NC;
-          w.p1 = cell + ((oi + 1) & 7) * DESC_NC;
-          w.dx = x1 ? 8 * DESC_NC : 0;
-          w.dy = y1 ? 32 * DESC_NC : 0;
-          const float a00 = __fmul_rn(wy0, wx0);
-          const float a01 = x1 ? __fmul_rn(wy0, xfrac) : 0.f;
-          const float a10 = y1 ? __fmul_rn(yfrac, wx0) : 0.f;
-          const float a11 = (x1 && y1) ? __fmul_rn(yfrac, xfrac) : 0.f;
+          const int o0 = (oi & 7) * DESC_NC, o1 = ((oi + 1) & 7) * DESC_NC;
+          const int cx = cell + 8 * DESC_NC, cy = cell + 32 * DESC_NC;
+          const int scratch = 128 * DESC_NC + lcopy;
+          w.a[0] = cell + o0;
+          w.a[1] = cell + o1;
+          w.a[2] = x1 ? cx + o0 : scratch + 2 * DESC_NC;
+          w.a[3] = x1 ? cx + o1 : scratch + 3 * DESC_NC;
+          w.a[4] = y1 ? cy + o0 : scratch + 4 * DESC_NC;
+          w.a[5] = y1 ? cy + o1 : scratch + 5 * DESC_NC;
+          w.a[6] = (x1 && y1) ? cy + 8 * DESC_NC + o0 : scratch + 6 * DESC_NC;
+          w.a[7] = (x1 && y1) ? cy + 8 * DESC_NC + o1 : scratch + 7 * DESC_NC;
+          const float a00 = __fmul_rn(wy0, wx0), a01 = __fmul_rn(wy0, xfrac);
+          const float a10 = __fmul_rn(yfrac, wx0), a11 = __fmul_rn(yfrac, xfrac);
           w.v[0] = __fmul_rn(a00, wo0);
           w.v[1] = __fmul_rn(a00, wo1);
           w.v[2] = __fmul_rn(a01, wo0);
@@ -382,20 +392,17 @@ namespace sb {
           w.v[7] = __fmul_rn(a11, wo1);
           return w;
         };
-        // the 8 bin updates of one sample, for the lanes whose turn it is
+        // the 8 bin updates of one sample, for the lanes whose turn it is: all loads, then all stores
         auto update = [&](const Weights& w, bool mine) {
           if (!mine)
             return;
-          float* q0 = priv + w.p0;
-          float* q1 = priv + w.p1;
-          q0[0] = __fadd_rn(q0[0], w.v[0]);
-          q1[0] = __fadd_rn(q1[0], w.v[1]);
-          q0[w.dx] = __fadd_rn(q0[w.dx], w.v[2]);
-          q1[w.dx] = __fadd_rn(q1[w.dx], w.v[3]);
-          q0[w.dy] = __fadd_rn(q0[w.dy], w.v[4]);
-          q1[w.dy] = __fadd_rn(q1[w.dy], w.v[5]);
-          q0[w.dx + w.dy] = __fadd_rn(q0[w.dx + w.dy], w.v[6]);
-          q1[w.dx + w.dy] = __fadd_rn(q1[w.dx + w.dy], w.v[7]);
+          float cur[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            cur[k] = priv[w.a[k]];
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            priv[w.a[k]] = __fadd_rn(cur[k], w.v[k]);
         };
         // Processes queue entries [0, m), m <= 96, three per lane with their loads overlapped.
         auto drain = [&](int m) {
@@ -539,7 +546,7 @@ namespace sb {
   int launch_descriptors(const PyramidDesc& P, const Keypoint* kp_oct, Keypoint* kp_out, float* desc,
                          int cap_kp, Counters* counters, cudaStream_t st)
   {
-    const int smem = DESC_WARPS * (128 * DESC_NC + 128) * sizeof(float);
+    const int smem = DESC_WARPS * (DESC_BINS * DESC_NC + 128) * sizeof(float);
     cudaFuncSetAttribute(descriptor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     descriptor_kernel<<<148 * 6, DESC_WARPS * 32, smem, st>>>(P, kp_oct, counters, cap_kp, kp_out, desc);
     return 1;

@@ -12,6 +12,8 @@
 // over when a later iteration leaves the domain).  Compiled with -fmad=false;
 // every decision is taken on bit-identical fp32 values, so the integer outputs
 // (x, y, s, o, type) are exact.
+#include <algorithm>
+
 #include "common.cuh"
 #include "scan.cuh"
 
@@ -25,27 +27,32 @@ namespace sb {
     }
 
     // ---- pass 1: classify every pixel of D(s, o), s = 1 .. n_scales - 3 ------
-    // Second half of LocalScaleSpaceExtremum + on_edge for a pixel that already is a
-    // non-strict extremum of its own layer and passed the threshold
-    // (RefineExtremum.cpp:407-437, Extrema.hpp:63-75).  Returns the uint8 map value.
-    __device__ __forceinline__ uint8_t classify_rest(const float* __restrict__ Dc, int layer_stride, int pitch, int x,
-                                                  int y, float v, bool is_max, bool is_min, float edge_ratio)
+    // All octaves and all scales in ONE streaming pass.  A warp owns a column block of 120
+    // pixels (32 lanes x 4 pixels, the first and last lane are halo lanes) and a segment of
+    // rows, and marches down: per step it loads one row of each DoG layer (16-byte loads),
+    // keeps three rows of every layer in registers, and decides the non-strict 3x3x3 test of
+    // LocalScaleSpaceExtremum (ImageProcessing/Extrema.hpp:28-75) for the three pixels-layers
+    // s = 1 .. n-3 from separable maxima / minima: v >= its 26 neighbours <=> v equals the
+    // maximum of the 27.  Every DoG layer is read once; nothing is staged in shared memory and
+    // no two warps talk to each other.  Survivors (rare) run the threshold and the edge test
+    // (RefineExtremum.cpp:407-437) on the spot.
+    constexpr int CLS_W = 120;     // pixels a warp classifies per row
+    constexpr int CLS_SEG = 48;    // rows per warp
+    constexpr int CLS_MAXL = 5;    // DoG layers of the default schedule (register-resident path)
+
+    struct ClassifyTiles
     {
-      const float* Dp = Dc - layer_stride;
-      const float* Dn = Dc + layer_stride;
-#pragma unroll
-      for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-        for (int dx = -1; dx <= 1; ++dx)
-        {
-          const float a = ld(Dp, pitch, x + dx, y + dy);
-          const float b = ld(Dn, pitch, x + dx, y + dy);
-          is_max = is_max && (v >= a) && (v >= b);
-          is_min = is_min && (v <= a) && (v <= b);
-        }
-      if (!(is_max || is_min))
-        return 0;
-      // on_edge(): Hessian functor, ImageProcessing/Differential.hpp:191-226.
+      int base[kMaxOctaves + 1];  // first warp of every octave
+      int n_cb[kMaxOctaves];      // column blocks of the octave
+    };
+
+    __device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+    __device__ __forceinline__ float min3(float a, float b, float c) { return fminf(fminf(a, b), c); }
+
+    // on_edge(): Hessian functor, ImageProcessing/Differential.hpp:191-226, RefineExtremum.cpp:24-30.
+    __device__ __forceinline__ bool on_edge_at(const float* __restrict__ Dc, int pitch, int x, int y, float v,
+                                               float edge_ratio)
+    {
       const float c2 = __fmul_rn(2.f, v);
       const float hxx = __fadd_rn(__fsub_rn(ld(Dc, pitch, x + 1, y), c2), ld(Dc, pitch, x - 1, y));
       const float hyy = __fadd_rn(__fsub_rn(ld(Dc, pitch, x, y + 1), c2), ld(Dc, pitch, x, y - 1));
@@ -57,146 +64,164 @@ namespace sb {
       const float tr = __fadd_rn(hxx, hyy);
       const float det = __fsub_rn(__fmul_rn(hxx, hyy), __fmul_rn(hxy, hxy));
       const float e1 = __fadd_rn(edge_ratio, 1.f);
-      const bool edge = __fmul_rn(__fmul_rn(tr, tr), edge_ratio) >= __fmul_rn(__fmul_rn(e1, e1), fabsf(det));
-      if (edge)
-        return 0;
-      return is_max ? 1 : 255;  // maximum is tested first (RefineExtremum.cpp:419-426)
+      return __fmul_rn(__fmul_rn(tr, tr), edge_ratio) >= __fmul_rn(__fmul_rn(e1, e1), fabsf(det));
     }
 
-    // All octaves and scales in one launch.  A block is a tile of 128 x 32 pixels of one DoG
-    // layer; a thread owns 4 x 4 pixels.  It loads the 6 x 4 centre-layer values it needs as
-    // float4 rows, takes the two halo columns from its neighbour lanes by warp shuffle, and
-    // decides "non-strict extremum of its own 3 x 3" for its 16 pixels from registers with
-    // running max / min (v >= all 8 neighbours <=> v >= their max).  Only the few survivors
-    // that also pass the threshold touch the two adjacent layers.
-    constexpr int CLS_RT = 4;  // rows per thread of classify_kernel (a block covers 128 x 8 * CLS_RT pixels)
-
-    struct ClassifyTiles
+    template <int NL>  // DoG layers per octave (n_scales - 1); NL - 2 of them are classified
+    __global__ void __launch_bounds__(128, 3)
+        classify_sweep_kernel(const __grid_constant__ PyramidDesc P, const __grid_constant__ ClassifyTiles Tl,
+                              const ExtremaParams ep)
     {
-      int base[kMaxOctaves + 1];  // first tile of every octave
-      int tiles_x[kMaxOctaves], tiles_y[kMaxOctaves];
-    };
-
-    __global__ void __launch_bounds__(256, 4)
-        classify_kernel(const __grid_constant__ PyramidDesc P, const __grid_constant__ ClassifyTiles T,
-                        const ExtremaParams ep)
-    {
+      const int lane = threadIdx.x & 31;
+      const int gw = blockIdx.x * 4 + (threadIdx.x >> 5);
+      if (gw >= Tl.base[P.n_octaves])
+        return;
       int o = 0;
-      while (o + 1 < P.n_octaves && static_cast<int>(blockIdx.x) >= T.base[o + 1])
+      while (o + 1 < P.n_octaves && gw >= Tl.base[o + 1])
         ++o;
       const OctaveDesc& oct = P.oct[o];
-      int tile = blockIdx.x - T.base[o];
-      const int per_layer = T.tiles_x[o] * T.tiles_y[o];
-      const int s = tile / per_layer + 1;
-      tile -= (s - 1) * per_layer;
-      const int ty = tile / T.tiles_x[o], tx = tile - ty * T.tiles_x[o];
-      const int lane = threadIdx.x;
-      const int x0 = (tx * 32 + lane) * 4;
-      const int yb = (ty * 8 + threadIdx.y) * CLS_RT;  // first of the thread's rows
+      const int local = gw - Tl.base[o];
+      const int sg = local / Tl.n_cb[o], cb = local - sg * Tl.n_cb[o];
       const int w = oct.w, h = oct.h, pitch = oct.pitch;
+      const int x0 = CLS_W * cb - 4 + 4 * lane;  // first of the lane's four pixels
+      const int ya = sg * CLS_SEG, yb = min(ya + CLS_SEG, h);
+      const bool ld_on = x0 >= 0 && x0 < w;      // the 16-byte load stays inside the padded row
+      const bool out_on = lane >= 1 && lane <= 30 && x0 < w;
       const float thr = __fmul_rn(0.8f, ep.extremum_thres);
-      const float* Dc = oct.D + static_cast<size_t>(s) * oct.layer_stride;
+      const float* const D0 = oct.D + x0;
+      const size_t ls = oct.layer_stride;
 
-      // Survivors of the in-layer test wait here; the whole block then finishes them together.
-      constexpr int LIST = 1024;
-      __shared__ int s_n;
-      __shared__ unsigned s_xy[LIST];     // x | y << 16
-      __shared__ float s_v[LIST];         // centre value, sign bit of the index word: polarity flags below
-      __shared__ unsigned char s_flag[LIST];  // bit 0: is_max, bit 1: is_min
-      if (threadIdx.x == 0 && threadIdx.y == 0)
-        s_n = 0;
-      __syncthreads();
-
-      if (yb < h)  // warp-uniform
-      {
-        // R[r][c]: rows yb - 1 .. yb + CLS_RT (clamped for the loads), columns x0 - 1 .. x0 + 4
-        float R[CLS_RT + 2][6];
-        const bool col_on = x0 < w;
+      float r[NL][3][4];  // [layer][row slot][pixel]
+      auto load_row = [&](int slot, int y) {
+        const bool on = ld_on && y >= 0 && y < h;
 #pragma unroll
-        for (int r = 0; r < CLS_RT + 2; ++r)
+        for (int L = 0; L < NL; ++L)
         {
-          const int yy = min(max(yb - 1 + r, 0), h - 1);
-          const float* row = Dc + static_cast<size_t>(yy) * pitch;
-          float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (col_on)
-            v4 = __ldg(reinterpret_cast<const float4*>(row + x0));
-          R[r][1] = v4.x;
-          R[r][2] = v4.y;
-          R[r][3] = v4.z;
-          R[r][4] = v4.w;
-          float left = __shfl_up_sync(0xffffffffu, v4.w, 1);
-          float right = __shfl_down_sync(0xffffffffu, v4.x, 1);
-          if (lane == 0)
-            left = (col_on && x0 > 0) ? __ldg(row + x0 - 1) : 0.f;
-          if (lane == 31)
-            right = (col_on && x0 + 4 < w) ? __ldg(row + x0 + 4) : 0.f;
-          R[r][0] = left;
-          R[r][5] = right;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (on)
+            v = __ldg(reinterpret_cast<const float4*>(D0 + L * ls + static_cast<size_t>(y) * pitch));
+          r[L][slot][0] = v.x;
+          r[L][slot][1] = v.y;
+          r[L][slot][2] = v.z;
+          r[L][slot][3] = v.w;
         }
-
+      };
+      // classify row y; its rows y - 1, y, y + 1 are in slots (mid + 2) % 3, mid, (mid + 1) % 3
+      auto classify_row = [&](int mid, int y) {
+        float hmx[NL][4], hmn[NL][4];
 #pragma unroll
-        for (int k = 0; k < CLS_RT; ++k)
+        for (int L = 0; L < NL; ++L)
         {
-          const int y = yb + k;
-          if (y >= h)
-            break;  // warp-uniform
-          // the map row starts empty; survivors are filled in below
-          if (x0 < oct.map_pitch)
-            *reinterpret_cast<uchar4*>(oct.map + (static_cast<size_t>(s - 1) * h + y) * oct.map_pitch + x0) =
-                make_uchar4(0, 0, 0, 0);
-          // column-wise max / min over rows y - 1, y, y + 1
           float cmx[6], cmn[6];
 #pragma unroll
-          for (int c = 0; c < 6; ++c)
+          for (int c = 0; c < 4; ++c)
           {
-            cmx[c] = fmaxf(fmaxf(R[k][c], R[k + 1][c]), R[k + 2][c]);
-            cmn[c] = fminf(fminf(R[k][c], R[k + 1][c]), R[k + 2][c]);
+            cmx[c + 1] = max3(r[L][0][c], r[L][1][c], r[L][2][c]);
+            cmn[c + 1] = min3(r[L][0][c], r[L][1][c], r[L][2][c]);
           }
-          const bool row_ok = col_on && ep.pad <= y && y < h - ep.pad;
+          cmx[0] = __shfl_up_sync(0xffffffffu, cmx[4], 1);
+          cmn[0] = __shfl_up_sync(0xffffffffu, cmn[4], 1);
+          cmx[5] = __shfl_down_sync(0xffffffffu, cmx[1], 1);
+          cmn[5] = __shfl_down_sync(0xffffffffu, cmn[1], 1);
 #pragma unroll
-          for (int e = 0; e < 4; ++e)
+          for (int c = 0; c < 4; ++c)
           {
-            const int c = e + 1, x = x0 + e;
-            const float v = R[k + 1][c];
-            const float nmax = fmaxf(fmaxf(cmx[c - 1], cmx[c + 1]), fmaxf(R[k][c], R[k + 2][c]));
-            const float nmin = fminf(fminf(cmn[c - 1], cmn[c + 1]), fminf(R[k][c], R[k + 2][c]));
-            const bool is_max = v >= nmax, is_min = v <= nmin;
-            // all the rejections are ANDed in the reference; the cheap ones go first
-            if (row_ok && ep.pad <= x && x < w - ep.pad && (is_max || is_min) && !(fabsf(v) < thr))
+            hmx[L][c] = max3(cmx[c], cmx[c + 1], cmx[c + 2]);
+            hmn[L][c] = min3(cmn[c], cmn[c + 1], cmn[c + 2]);
+          }
+        }
+        const bool row_ok = ep.pad <= y && y < h - ep.pad;
+#pragma unroll
+        for (int s = 1; s <= NL - 2; ++s)
+        {
+          unsigned char t4[4] = {0, 0, 0, 0};
+          int n_mine = 0;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+          {
+            const float v = r[s][mid][c];
+            const float M = max3(hmx[s - 1][c], hmx[s][c], hmx[s + 1][c]);
+            const float m = min3(hmn[s - 1][c], hmn[s][c], hmn[s + 1][c]);
+            const bool is_max = v >= M, is_min = v <= m;
+            const int x = x0 + c;
+            if ((is_max || is_min) && row_ok && out_on && ep.pad <= x && x < w - ep.pad && !(fabsf(v) < thr))
             {
-              const int slot = atomicAdd(&s_n, 1);
-              if (slot < LIST)
+              // rare: the edge test reads its 3x3 from the layer (L1 / L2 hits)
+              if (!on_edge_at(oct.D + s * ls, pitch, x, y, v, ep.edge_ratio))
               {
-                s_xy[slot] = static_cast<unsigned>(x) | (static_cast<unsigned>(y) << 16);
-                s_v[slot] = v;
-                s_flag[slot] = static_cast<unsigned char>((is_max ? 1 : 0) | (is_min ? 2 : 0));
-              }
-              else
-              {
-                // list full (never seen on natural images): finish this one on the spot
-                const uint8_t t = classify_rest(Dc, oct.layer_stride, pitch, x, y, v, is_max, is_min, ep.edge_ratio);
-                if (t != 0)
-                {
-                  oct.map[(static_cast<size_t>(s - 1) * h + y) * oct.map_pitch + x] = t;
-                  atomicAdd(oct.row_count + (s - 1) * h + y, 1);
-                }
+                t4[c] = is_max ? 1 : 255;  // the maximum is tested first (RefineExtremum.cpp:419-426)
+                ++n_mine;
               }
             }
           }
+          if (out_on)
+            *reinterpret_cast<uchar4*>(oct.map + (static_cast<size_t>(s - 1) * h + y) * oct.map_pitch + x0) =
+                make_uchar4(t4[0], t4[1], t4[2], t4[3]);
+          const unsigned any = __ballot_sync(0xffffffffu, n_mine != 0);
+          if (any)
+          {
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1)
+              n_mine += __shfl_xor_sync(0xffffffffu, n_mine, d);
+            if (lane == 0)
+              atomicAdd(oct.row_count + (s - 1) * h + y, n_mine);
+          }
         }
-      }
-      __syncthreads();
-      const int n_list = min(s_n, LIST);
-      for (int i = threadIdx.y * 32 + threadIdx.x; i < n_list; i += 256)
+      };
+
+      load_row(0, ya - 1);
+      load_row(1, ya);
+      for (int y = ya; y < yb; y += 3)
       {
-        const int x = static_cast<int>(s_xy[i] & 0xffffu), y = static_cast<int>(s_xy[i] >> 16);
-        const uint8_t t = classify_rest(Dc, oct.layer_stride, pitch, x, y, s_v[i], (s_flag[i] & 1) != 0,
-                                        (s_flag[i] & 2) != 0, ep.edge_ratio);
-        if (t != 0)
+        load_row(2, y + 1);
+        classify_row(1, y);
+        if (y + 1 >= yb)
+          break;
+        load_row(0, y + 2);
+        classify_row(2, y + 1);
+        if (y + 2 >= yb)
+          break;
+        load_row(1, y + 3);
+        classify_row(0, y + 2);
+      }
+    }
+
+    // Any other number of layers: one thread per pixel, straight from global memory.
+    __global__ void __launch_bounds__(256)
+        classify_generic_kernel(const __grid_constant__ PyramidDesc P, int o, const ExtremaParams ep)
+    {
+      const OctaveDesc& oct = P.oct[o];
+      const int w = oct.w, h = oct.h, pitch = oct.pitch;
+      const int n_s = P.n_scales - 3;
+      const float thr = __fmul_rn(0.8f, ep.extremum_thres);
+      const long long n = static_cast<long long>(w) * h * n_s;
+      for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+           i += static_cast<long long>(gridDim.x) * blockDim.x)
+      {
+        const int x = static_cast<int>(i % w);
+        const int y = static_cast<int>((i / w) % h);
+        const int s = static_cast<int>(i / (static_cast<long long>(w) * h)) + 1;
+        uint8_t t = 0;
+        if (ep.pad <= x && x < w - ep.pad && ep.pad <= y && y < h - ep.pad)
         {
-          oct.map[(static_cast<size_t>(s - 1) * h + y) * oct.map_pitch + x] = t;
-          atomicAdd(oct.row_count + (s - 1) * h + y, 1);
+          const float* Dc = oct.D + static_cast<size_t>(s) * oct.layer_stride;
+          const float v = ld(Dc, pitch, x, y);
+          bool is_max = true, is_min = true;
+          for (int ds = -1; ds <= 1; ++ds)
+            for (int dy = -1; dy <= 1; ++dy)
+              for (int dx = -1; dx <= 1; ++dx)
+              {
+                const float a = ld(Dc + ds * static_cast<long long>(oct.layer_stride), pitch, x + dx, y + dy);
+                is_max = is_max && v >= a;
+                is_min = is_min && v <= a;
+              }
+          if ((is_max || is_min) && !(fabsf(v) < thr) && !on_edge_at(Dc, pitch, x, y, v, ep.edge_ratio))
+          {
+            t = is_max ? 1 : 255;
+            atomicAdd(oct.row_count + (s - 1) * h + y, 1);
+          }
         }
+        oct.map[(static_cast<size_t>(s - 1) * h + y) * oct.map_pitch + x] = t;
       }
     }
 
@@ -541,20 +566,32 @@ namespace sb {
   int launch_classify(const PyramidDesc& P, const ExtremaParams& ep, int n_segments, int o_lo, int o_hi,
                       bool zero_counts, cudaStream_t st)
   {
-    const int n_s = P.n_scales - 3;
     if (zero_counts)
       cudaMemsetAsync(P.oct[0].row_count, 0, sizeof(int) * n_segments, st);
+    const int n_layers = P.n_scales - 1;
+    if (n_layers != CLS_MAXL)
+    {
+      int launches = 0;
+      for (int o = o_lo; o < o_hi && o < P.n_octaves; ++o)
+      {
+        const long long n = static_cast<long long>(P.oct[o].w) * P.oct[o].h * (P.n_scales - 3);
+        const int blocks = static_cast<int>(std::min<long long>((n + 255) / 256, 148 * 16));
+        classify_generic_kernel<<<std::max(blocks, 1), 256, 0, st>>>(P, o, ep);
+        ++launches;
+      }
+      return launches;
+    }
     ClassifyTiles T{};
     for (int o = 0; o < P.n_octaves; ++o)
     {
       const bool in = o >= o_lo && o < o_hi;
-      T.tiles_x[o] = (P.oct[o].w + 127) / 128;
-      T.tiles_y[o] = (P.oct[o].h + 8 * CLS_RT - 1) / (8 * CLS_RT);
-      T.base[o + 1] = T.base[o] + (in ? T.tiles_x[o] * T.tiles_y[o] * n_s : 0);
+      T.n_cb[o] = (P.oct[o].w + CLS_W - 1) / CLS_W;
+      const int n_sg = (P.oct[o].h + CLS_SEG - 1) / CLS_SEG;
+      T.base[o + 1] = T.base[o] + (in ? T.n_cb[o] * n_sg : 0);
     }
     if (T.base[P.n_octaves] == 0)
       return 0;
-    classify_kernel<<<T.base[P.n_octaves], dim3(32, 8), 0, st>>>(P, T, ep);
+    classify_sweep_kernel<CLS_MAXL><<<(T.base[P.n_octaves] + 3) / 4, 128, 0, st>>>(P, T, ep);
     return 1;
   }
 

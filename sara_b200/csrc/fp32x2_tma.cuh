@@ -78,6 +78,14 @@ namespace sb {
     }
 
 
+    __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int x, int y)
+    {
+      asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(
+                       reinterpret_cast<unsigned long long>(map)),
+                   "r"(x), "r"(y)
+                   : "memory");
+    }
+
     // ---- cp.async (LDGSTS): 8-byte global -> shared copies, completion by commit groups -----
     __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc)
     {

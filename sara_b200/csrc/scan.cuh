@@ -88,6 +88,38 @@ namespace sb {
       }
     }
 
+    // Small arrays (the usual case: row counters, keep flags, orientation counts): one block,
+    // one launch.  Thread t owns the slice [t m, (t + 1) m); final offsets go to out_off and the
+    // chunk offsets are zero, so consumers keep using out_off[i] + chunk_off[i >> 10].
+    static __global__ void __launch_bounds__(1024)
+        scan_single_kernel(const int* __restrict__ vals, int* __restrict__ out_off, int* __restrict__ chunk_off,
+                           int n_static, const int* __restrict__ n_ptr, int n_cap, int* __restrict__ total_out,
+                           int total_cap, int* __restrict__ overflow, int overflow_bit)
+    {
+      __shared__ int total;
+      const int n = n_ptr ? min(*n_ptr, n_cap) : n_static;
+      const int m = (n + 1023) >> 10;
+      const int lo = min(static_cast<int>(threadIdx.x) * m, n), hi = min(lo + m, n);
+      int sum = 0;
+      for (int i = lo; i < hi; ++i)
+        sum += vals[i];
+      int run = block_exclusive_scan_1024(sum, &total);
+      for (int i = lo; i < hi; ++i)
+      {
+        const int v = vals[i];
+        out_off[i] = run;
+        run += v;
+      }
+      for (int c = threadIdx.x; c <= (n >> 10); c += 1024)
+        chunk_off[c] = 0;
+      if (threadIdx.x == 0)
+      {
+        if (total > total_cap)
+          atomicOr(overflow, overflow_bit);
+        *total_out = total;  // the true count; consumers clamp to their capacity
+      }
+    }
+
   }  // namespace scan_detail
 
   // Returns the number of kernels launched.
@@ -96,6 +128,12 @@ namespace sb {
                                    int* overflow, int overflow_bit, cudaStream_t st)
   {
     const int max_n = n_ptr ? n_cap : n_static;
+    if (max_n <= (1 << 20) && vals != out_off)
+    {
+      scan_detail::scan_single_kernel<<<1, 1024, 0, st>>>(vals, out_off, chunk_off, n_static, n_ptr, n_cap, total_out,
+                                                          total_cap, overflow, overflow_bit);
+      return 1;
+    }
     int grid = (max_n + 1023) >> 10;
     if (grid < 1)
       grid = 1;

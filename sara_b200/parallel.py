@@ -86,6 +86,62 @@ def gather_keypoint_lists(local: dict, dst: int = 0, group=None, device=None):
     return out
 
 
+def gather_keypoint_tensors(local: dict, dst: int = 0, group=None):
+    """Gathers {frame_index: (keypoints, descriptors)} onto `dst` WITHOUT leaving the device:
+    keypoints are (n, 52) uint8 tensors (KEYPOINT_DTYPE records), descriptors (n, 128) float32
+    tensors, both on this rank's device (CUDA + NCCL in production, CPU + gloo in the tests).
+    Counts travel first (one all_gather of a fixed-size int64 table), then every rank
+    contributes one flat byte buffer padded to the longest (dist.gather); `dst` slices the
+    frames back out as views of the gathered buffers.  Returns the merged dict on `dst`, None
+    elsewhere.  SURVEY.md section 8e."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    frames = sorted(local)
+    dev = local[frames[0]][1].device if frames else torch.device("cpu")
+
+    n_local = torch.tensor([len(frames)], dtype=torch.int64, device=dev)
+    all_n = [torch.zeros_like(n_local) for _ in range(world)]
+    dist.all_gather(all_n, n_local, group=group)
+    max_frames = max(int(t.item()) for t in all_n)
+    table = torch.zeros((max(max_frames, 1), 2), dtype=torch.int64, device=dev)  # (frame, count)
+    for i, f in enumerate(frames):
+        table[i, 0], table[i, 1] = f, local[f][0].shape[0]
+    all_tab = [torch.zeros_like(table) for _ in range(world)]
+    dist.all_gather(all_tab, table, group=group)
+    all_tab = [t.cpu().numpy() for t in all_tab]
+    rec = 52 + 512
+    totals = [int(all_tab[r][: int(all_n[r].item()), 1].sum()) * rec for r in range(world)]
+    max_bytes = max(max(totals), 1)
+
+    buf = torch.zeros(max_bytes, dtype=torch.uint8, device=dev)
+    off = 0
+    for f in frames:
+        kp, desc = local[f]
+        n = kp.shape[0]
+        buf[off: off + 52 * n] = kp.reshape(-1)
+        off += 52 * n
+        buf[off: off + 512 * n] = desc.contiguous().view(torch.uint8).reshape(-1)
+        off += 512 * n
+    gathered = [torch.zeros_like(buf) for _ in range(world)] if rank == dst else None
+    dist.gather(buf, gathered, dst=dst, group=group)
+    if rank != dst:
+        return None
+    out = {}
+    for r in range(world):
+        off = 0
+        for i in range(int(all_n[r].item())):
+            f, n = int(all_tab[r][i, 0]), int(all_tab[r][i, 1])
+            kp = gathered[r][off: off + 52 * n].view(n, 52)
+            off += 52 * n
+            desc = gathered[r][off: off + 512 * n].view(torch.float32).view(n, 128)
+            off += 512 * n
+            out[f] = (kp, desc)
+    return out
+
+
 def reduce_throughput(n_keypoints: int, seconds: float, device=None, group=None):
     """(sum of keypoints over ranks, max of the elapsed time over ranks)."""
     import torch

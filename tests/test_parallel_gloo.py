@@ -31,6 +31,12 @@ def _worker(rank, world, port, q):
     mine = P.shard_frames(7, rank, world)
     local = {f: _fake_result(f) for f in mine}
     merged = P.gather_keypoint_lists(local, dst=0)
+    # the tensor path (NCCL from device buffers in production; CPU tensors over gloo here)
+    import torch
+
+    local_t = {f: (torch.from_numpy(np.frombuffer(k.tobytes(), np.uint8).reshape(-1, 52).copy()), torch.from_numpy(d))
+               for f, (k, d) in local.items()}
+    merged_t = P.gather_keypoint_tensors(local_t, dst=0)
     n_local = sum(len(v[0]) for v in local.values())
     tot, mx = P.reduce_throughput(n_local, 1.0 + rank)
     ok = True
@@ -39,9 +45,10 @@ def _worker(rank, world, port, q):
         for f in range(7):
             k, d = _fake_result(f)
             ok = ok and merged[f][0].tobytes() == k.tobytes() and merged[f][1].tobytes() == d.tobytes()
+            ok = ok and merged_t[f][0].numpy().tobytes() == k.tobytes() and merged_t[f][1].numpy().tobytes() == d.tobytes()
         ok = ok and tot == sum(len(_fake_result(f)[0]) for f in range(7)) and mx == float(world)
     else:
-        ok = merged is None
+        ok = merged is None and merged_t is None
     q.put((rank, ok))
     dist.destroy_process_group()
 
