@@ -499,15 +499,17 @@ def compute_sift_keypoints(image, pyramid_params: ImagePyramidParams | None = No
                            extremum_refinement_iter: int = 5, parallel: bool = True, device: int = 0) -> KeypointList:
     """pysara.compute_sift_keypoints (pybind11/FeatureDetectors.cpp:116-124), same
     argument order and defaults; `parallel` is accepted and ignored (the GPU path is
-    always parallel)."""
-    _, w, h, _, _ = _as_image(image)
-    key = device
-    ctx = _DEFAULT_CTX.get(key)
+    always parallel).  One context per device is kept, sized for the largest width and the
+    largest height seen so far (frames of alternating orientation do not recreate it)."""
+    ptr, w, h, on_dev, keep = _as_image(image)
+    ctx = _DEFAULT_CTX.get(device)
     if ctx is None or ctx._w < w or ctx._h < h:
+        mw, mh = (max(w, ctx._w), max(h, ctx._h)) if ctx is not None else (w, h)
         if ctx is not None:
             ctx.close()
-        ctx = SiftContext(w, h, device)
-        ctx._w, ctx._h = w, h
-        _DEFAULT_CTX[key] = ctx
-    return ctx.compute_sift_keypoints(image, pyramid_params, gauss_truncate, extremum_thres, edge_ratio_thres,
+        ctx = SiftContext(mw, mh, device)
+        ctx._w, ctx._h = mw, mh
+        _DEFAULT_CTX[device] = ctx
+    # `keep` is the converted array / tensor: handed on as is, no second conversion
+    return ctx.compute_sift_keypoints(keep, pyramid_params, gauss_truncate, extremum_thres, edge_ratio_thres,
                                       extremum_refinement_iter)

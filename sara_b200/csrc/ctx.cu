@@ -126,6 +126,27 @@ namespace {
                   "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);     \
   } while (0)
 
+  // The API calls run on the context's device and leave the caller's current device as it was.
+  struct DeviceGuard
+  {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int device)
+    {
+      if (cudaGetDevice(&prev) != cudaSuccess)
+        prev = -1;
+      if (prev != device)
+        err = cudaSetDevice(device);
+      else
+        prev = -1;  // nothing to restore
+    }
+    ~DeviceGuard()
+    {
+      if (prev >= 0)
+        cudaSetDevice(prev);
+    }
+  };
+
   size_t align_up(size_t v, size_t a)
   {
     return (v + a - 1) / a * a;
@@ -766,7 +787,8 @@ int sara_b200_create(int device, const sara_b200_limits* limits, sara_b200_ctx**
     return fail(nullptr, SARA_B200_ERR_BAD_ARG, "device %d out of range [0, %d)", device, n_dev);
   if (limits->max_width <= 0 || limits->max_height <= 0)
     return fail(nullptr, SARA_B200_ERR_BAD_ARG, "limits: max_width / max_height must be positive");
-  CU(nullptr, cudaSetDevice(device));
+  DeviceGuard guard(device);
+  CU(nullptr, guard.err);
 
   auto* ctx = new sara_b200_ctx;
   ctx->device = device;
@@ -874,7 +896,7 @@ void sara_b200_destroy(sara_b200_ctx* ctx)
 {
   if (!ctx)
     return;
-  cudaSetDevice(ctx->device);
+  DeviceGuard guard(ctx->device);
   for (Slot& S : ctx->slots)
   {
     if (S.own_stream)
@@ -992,7 +1014,8 @@ static int sift_enqueue_impl(sara_b200_ctx* ctx, int slot, const void* image, in
     return fail(ctx, SARA_B200_ERR_TOO_FEW_SCALES,
                 "Error: The extraction of DoG extrema needs (1 + 3) = 4 scales per octave at the very "
                 "minimum!");
-  CU(ctx, cudaSetDevice(ctx->device));
+  DeviceGuard guard(ctx->device);
+  CU(ctx, guard.err);
   cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : S.own_stream;
   if (args->extremum_refinement_iter < 1)  // it becomes img_padding_sz (quirk N1); checked before any launch
     return fail(ctx, SARA_B200_ERR_BAD_ARG,
@@ -1275,7 +1298,8 @@ int sara_b200_dog_extrema(sara_b200_ctx* ctx, int slot, const float* image, int 
     return fail(ctx, SARA_B200_ERR_TOO_FEW_SCALES,
                 "Error: The extraction of DoG extrema needs (1 + 3) = 4 scales per octave at the very "
                 "minimum!");
-  CU(ctx, cudaSetDevice(ctx->device));
+  DeviceGuard guard(ctx->device);
+  CU(ctx, guard.err);
   cudaStream_t st = S.own_stream;
   if (args->img_padding_sz < 1)
     return fail(ctx, SARA_B200_ERR_BAD_ARG,
@@ -1309,7 +1333,8 @@ int sara_b200_pyramid_enqueue(sara_b200_ctx* ctx, int slot, const float* image, 
   Slot& S = ctx->slots[slot];
   if (S.busy)
     return fail(ctx, SARA_B200_ERR_BUSY, "slot %d holds an un-collected frame", slot);
-  CU(ctx, cudaSetDevice(ctx->device));
+  DeviceGuard guard(ctx->device);
+  CU(ctx, guard.err);
   cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : S.own_stream;
   rc = enqueue_pyramid(ctx, S, image, w, h, image_on_device != 0, *params, gauss_truncate, st);
   if (rc)
@@ -1410,7 +1435,8 @@ int sara_b200_gaussian(sara_b200_ctx* ctx, const float* src, int w, int h, float
   Taps taps;
   if (make_taps(sigma, gauss_truncate, &taps) < 0)
     return fail(ctx, SARA_B200_ERR_BAD_ARG, "Gaussian kernel exceeds %d taps", kMaxTaps);
-  CU(ctx, cudaSetDevice(ctx->device));
+  DeviceGuard guard(ctx->device);
+  CU(ctx, guard.err);
   const size_t bytes = sizeof(float) * w * h;
   int rc = grow_scratch(ctx, 2 * align_up(bytes, 256));
   if (rc)
@@ -1431,7 +1457,8 @@ int sara_b200_to_gray32f(sara_b200_ctx* ctx, const uint8_t* src, int w, int h, i
     return fail(nullptr, SARA_B200_ERR_BAD_ARG, "null context");
   if (!src || !dst || w <= 0 || h <= 0 || (channels != 1 && channels != 3))
     return fail(ctx, SARA_B200_ERR_BAD_ARG, "to_gray32f: bad arguments");
-  CU(ctx, cudaSetDevice(ctx->device));
+  DeviceGuard guard(ctx->device);
+  CU(ctx, guard.err);
   const size_t n = static_cast<size_t>(w) * h;
   const size_t in_bytes = align_up(n * channels, 256);
   int rc = grow_scratch(ctx, in_bytes + sizeof(float) * n);

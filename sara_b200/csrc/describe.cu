@@ -447,10 +447,19 @@ namespace sb {
             uv = (u & 0xffff) | (v << 16);
           }
           u += 32;
-          while (u > rounded_r)
+          if (side >= 32)  // warp-uniform: the usual case, a single wrap
           {
-            u -= side;
-            ++v;
+            const bool wrap = u > rounded_r;
+            u -= wrap ? side : 0;
+            v += wrap ? 1 : 0;
+          }
+          else
+          {
+            while (u > rounded_r)
+            {
+              u -= side;
+              ++v;
+            }
           }
           const unsigned m = __ballot_sync(0xffffffffu, keep);
           if (keep)

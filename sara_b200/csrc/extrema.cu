@@ -29,15 +29,17 @@ namespace sb {
     // ---- pass 1: classify every pixel of D(s, o), s = 1 .. n_scales - 3 ------
     // All octaves and all scales in ONE streaming pass.  A warp owns a column block of 120
     // pixels (32 lanes x 4 pixels, the first and last lane are halo lanes) and a segment of
-    // rows, and marches down: per step it loads one row of each DoG layer (16-byte loads),
-    // keeps three rows of every layer in registers, and decides the non-strict 3x3x3 test of
-    // LocalScaleSpaceExtremum (ImageProcessing/Extrema.hpp:28-75) for the three pixels-layers
-    // s = 1 .. n-3 from separable maxima / minima: v >= its 26 neighbours <=> v equals the
-    // maximum of the 27.  Every DoG layer is read once; nothing is staged in shared memory and
-    // no two warps talk to each other.  Survivors (rare) run the threshold and the edge test
-    // (RefineExtremum.cpp:407-437) on the spot.
+    // rows, and marches down: per step it loads one row of each of the MIDDLE DoG layers
+    // 1 .. n-2 (16-byte loads, issued one row ahead), keeps three rows of each in registers and
+    // decides the non-strict 3x3x3 test of LocalScaleSpaceExtremum
+    // (ImageProcessing/Extrema.hpp:28-75) from separable maxima / minima: v >= its neighbours
+    // <=> v equals the maximum over them and itself.  The scales next to the outer layers
+    // (s = 1 and s = n-2) are decided on the streamed layers first; the few survivors read the
+    // 3x3 of the outer layer, the threshold and the edge test (RefineExtremum.cpp:407-437) in a
+    // separate, rarely executed routine.  Nothing is staged in shared memory and no two warps
+    // talk to each other.
     constexpr int CLS_W = 120;     // pixels a warp classifies per row
-    constexpr int CLS_SEG = 48;    // rows per warp
+    constexpr int CLS_SEG = 32;    // rows per warp
     constexpr int CLS_MAXL = 5;    // DoG layers of the default schedule (register-resident path)
 
     struct ClassifyTiles
@@ -67,11 +69,38 @@ namespace sb {
       return __fmul_rn(__fmul_rn(tr, tr), edge_ratio) >= __fmul_rn(__fmul_rn(e1, e1), fabsf(det));
     }
 
-    template <int NL>  // DoG layers per octave (n_scales - 1); NL - 2 of them are classified
-    __global__ void __launch_bounds__(128, 3)
+    // The rare path: a pixel that is an extremum of the streamed layers and passes the threshold.
+    // `outer` (or nullptr): the layer whose 3x3 neighbourhood still has to be compared.  Returns the
+    // uint8 map value (1 maximum, 255 minimum: the reference stores -1 in an Image<uint8_t>, quirk
+    // N2; the maximum is tested first, RefineExtremum.cpp:419-426).
+    __device__ __noinline__ int finish_candidate(const float* __restrict__ Dc, const float* __restrict__ outer,
+                                                 int pitch, int x, int y, float v, int flags, float edge_ratio)
+    {
+      bool is_max = (flags & 1) != 0, is_min = (flags & 2) != 0;
+      if (outer != nullptr)
+      {
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+          for (int dx = -1; dx <= 1; ++dx)
+          {
+            const float a = ld(outer, pitch, x + dx, y + dy);
+            is_max = is_max && v >= a;
+            is_min = is_min && v <= a;
+          }
+      }
+      if (!(is_max || is_min) || on_edge_at(Dc, pitch, x, y, v, edge_ratio))
+        return 0;
+      return is_max ? 1 : 255;
+    }
+
+    template <int NL>  // DoG layers per octave (n_scales - 1); layers 1 .. NL - 2 are streamed and classified
+    __global__ void __launch_bounds__(128, 4)
         classify_sweep_kernel(const __grid_constant__ PyramidDesc P, const __grid_constant__ ClassifyTiles Tl,
                               const ExtremaParams ep)
     {
+      constexpr int NM = NL - 2;  // streamed (middle) layers; r[m] is DoG layer m + 1
+      static_assert(NM >= 2, "each classified layer has at most one outer neighbour");
       const int lane = threadIdx.x & 31;
       const int gw = blockIdx.x * 4 + (threadIdx.x >> 5);
       if (gw >= Tl.base[P.n_octaves])
@@ -88,36 +117,37 @@ namespace sb {
       const bool ld_on = x0 >= 0 && x0 < w;      // the 16-byte load stays inside the padded row
       const bool out_on = lane >= 1 && lane <= 30 && x0 < w;
       const float thr = __fmul_rn(0.8f, ep.extremum_thres);
-      const float* const D0 = oct.D + x0;
       const size_t ls = oct.layer_stride;
+      const float* const D1 = oct.D + ls + x0;   // layer 1 at the lane's first pixel
 
-      float r[NL][3][4];  // [layer][row slot][pixel]
+      float r[NM][4][4];  // [middle layer][row slot][pixel]: three rows in use, the fourth being loaded
       auto load_row = [&](int slot, int y) {
         const bool on = ld_on && y >= 0 && y < h;
 #pragma unroll
-        for (int L = 0; L < NL; ++L)
+        for (int m = 0; m < NM; ++m)
         {
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
           if (on)
-            v = __ldg(reinterpret_cast<const float4*>(D0 + L * ls + static_cast<size_t>(y) * pitch));
-          r[L][slot][0] = v.x;
-          r[L][slot][1] = v.y;
-          r[L][slot][2] = v.z;
-          r[L][slot][3] = v.w;
+            v = __ldg(reinterpret_cast<const float4*>(D1 + m * ls + static_cast<size_t>(y) * pitch));
+          r[m][slot][0] = v.x;
+          r[m][slot][1] = v.y;
+          r[m][slot][2] = v.z;
+          r[m][slot][3] = v.w;
         }
       };
-      // classify row y; its rows y - 1, y, y + 1 are in slots (mid + 2) % 3, mid, (mid + 1) % 3
+      // classify row y; its rows y - 1, y, y + 1 are in slots (mid + 3) % 4, mid, (mid + 1) % 4
       auto classify_row = [&](int mid, int y) {
-        float hmx[NL][4], hmn[NL][4];
+        const int up = (mid + 3) & 3, dn = (mid + 1) & 3;
+        float hmx[NM][4], hmn[NM][4];
 #pragma unroll
-        for (int L = 0; L < NL; ++L)
+        for (int m = 0; m < NM; ++m)
         {
           float cmx[6], cmn[6];
 #pragma unroll
           for (int c = 0; c < 4; ++c)
           {
-            cmx[c + 1] = max3(r[L][0][c], r[L][1][c], r[L][2][c]);
-            cmn[c + 1] = min3(r[L][0][c], r[L][1][c], r[L][2][c]);
+            cmx[c + 1] = max3(r[m][up][c], r[m][mid][c], r[m][dn][c]);
+            cmn[c + 1] = min3(r[m][up][c], r[m][mid][c], r[m][dn][c]);
           }
           cmx[0] = __shfl_up_sync(0xffffffffu, cmx[4], 1);
           cmn[0] = __shfl_up_sync(0xffffffffu, cmn[4], 1);
@@ -126,63 +156,87 @@ namespace sb {
 #pragma unroll
           for (int c = 0; c < 4; ++c)
           {
-            hmx[L][c] = max3(cmx[c], cmx[c + 1], cmx[c + 2]);
-            hmn[L][c] = min3(cmn[c], cmn[c + 1], cmn[c + 2]);
+            hmx[m][c] = max3(cmx[c], cmx[c + 1], cmx[c + 2]);
+            hmn[m][c] = min3(cmn[c], cmn[c + 1], cmn[c + 2]);
           }
         }
-        const bool row_ok = ep.pad <= y && y < h - ep.pad;
+        const bool row_ok = ep.pad <= y && y < h - ep.pad && out_on;
+        // bit 4 m + c: pixel c of scale s = m + 1 is a maximum / minimum of the streamed layers and
+        // passes the cheap rejections (all the rejections are ANDed in the reference)
+        unsigned mx_mask = 0u, mn_mask = 0u;
 #pragma unroll
-        for (int s = 1; s <= NL - 2; ++s)
-        {
-          unsigned char t4[4] = {0, 0, 0, 0};
-          int n_mine = 0;
+        for (int m = 0; m < NM; ++m)
 #pragma unroll
           for (int c = 0; c < 4; ++c)
           {
-            const float v = r[s][mid][c];
-            const float M = max3(hmx[s - 1][c], hmx[s][c], hmx[s + 1][c]);
-            const float m = min3(hmn[s - 1][c], hmn[s][c], hmn[s + 1][c]);
-            const bool is_max = v >= M, is_min = v <= m;
-            const int x = x0 + c;
-            if ((is_max || is_min) && row_ok && out_on && ep.pad <= x && x < w - ep.pad && !(fabsf(v) < thr))
+            const float v = r[m][mid][c];
+            float M = hmx[m][c], mn = hmn[m][c];
+            if (m > 0)
             {
-              // rare: the edge test reads its 3x3 from the layer (L1 / L2 hits)
-              if (!on_edge_at(oct.D + s * ls, pitch, x, y, v, ep.edge_ratio))
-              {
-                t4[c] = is_max ? 1 : 255;  // the maximum is tested first (RefineExtremum.cpp:419-426)
-                ++n_mine;
-              }
+              M = fmaxf(M, hmx[m - 1][c]);
+              mn = fminf(mn, hmn[m - 1][c]);
             }
+            if (m + 1 < NM)
+            {
+              M = fmaxf(M, hmx[m + 1][c]);
+              mn = fminf(mn, hmn[m + 1][c]);
+            }
+            const int x = x0 + c;
+            const bool live = row_ok && ep.pad <= x && x < w - ep.pad && !(fabsf(v) < thr);
+            if (live && v >= M)
+              mx_mask |= 1u << (4 * m + c);
+            if (live && v <= mn)
+              mn_mask |= 1u << (4 * m + c);
           }
-          if (out_on)
-            *reinterpret_cast<uchar4*>(oct.map + (static_cast<size_t>(s - 1) * h + y) * oct.map_pitch + x0) =
-                make_uchar4(t4[0], t4[1], t4[2], t4[3]);
-          const unsigned any = __ballot_sync(0xffffffffu, n_mine != 0);
-          if (any)
-          {
+        if (out_on)
+        {
 #pragma unroll
-            for (int d = 16; d > 0; d >>= 1)
-              n_mine += __shfl_xor_sync(0xffffffffu, n_mine, d);
-            if (lane == 0)
-              atomicAdd(oct.row_count + (s - 1) * h + y, n_mine);
+          for (int m = 0; m < NM; ++m)
+            *reinterpret_cast<uchar4*>(oct.map + (static_cast<size_t>(m) * h + y) * oct.map_pitch + x0) =
+                make_uchar4(0, 0, 0, 0);
+        }
+        // the few survivors, one per lane and round
+        unsigned pend = mx_mask | mn_mask;
+        while (__any_sync(0xffffffffu, pend != 0u))
+        {
+          if (pend != 0u)
+          {
+            const int b = __ffs(pend) - 1;
+            pend &= pend - 1u;
+            const int m = b >> 2, x = x0 + (b & 3);
+            const float* Dc = oct.D + (m + 1) * ls;
+            const float* outer = m == 0 ? oct.D : (m == NM - 1 ? oct.D + (NL - 1) * ls : nullptr);
+            const int flags = ((mx_mask >> b) & 1u) | (((mn_mask >> b) & 1u) << 1);
+            const int t = finish_candidate(Dc, outer, pitch, x, y, ld(Dc, pitch, x, y), flags, ep.edge_ratio);
+            if (t != 0)
+            {
+              oct.map[(static_cast<size_t>(m) * h + y) * oct.map_pitch + x] = static_cast<uint8_t>(t);
+              atomicAdd(oct.row_count + m * h + y, 1);
+            }
           }
         }
       };
 
+      // the loads of row y + 2 are in flight while row y is classified
       load_row(0, ya - 1);
       load_row(1, ya);
-      for (int y = ya; y < yb; y += 3)
+      load_row(2, ya + 1);
+      for (int y = ya; y < yb; y += 4)
       {
-        load_row(2, y + 1);
+        load_row(3, y + 2);
         classify_row(1, y);
         if (y + 1 >= yb)
           break;
-        load_row(0, y + 2);
+        load_row(0, y + 3);
         classify_row(2, y + 1);
         if (y + 2 >= yb)
           break;
-        load_row(1, y + 3);
-        classify_row(0, y + 2);
+        load_row(1, y + 4);
+        classify_row(3, y + 2);
+        if (y + 3 >= yb)
+          break;
+        load_row(2, y + 5);
+        classify_row(0, y + 3);
       }
     }
 
@@ -609,7 +663,9 @@ namespace sb {
 
     launches += exclusive_scan(P.oct[0].row_count, seg_offsets, chunk_off, n_segments, nullptr, 0,
                                &counters->n_cand, cap_cand, &counters->overflow, 1, st);
-    compact_rows_kernel<<<296, 256, 0, st>>>(P, n_segments, seg_offsets, chunk_off, cand, cap_cand);
+    // one warp per raster row of every classified layer
+    compact_rows_kernel<<<std::max(1, std::min((n_segments + 7) / 8, 148 * 16)), 256, 0, st>>>(P, n_segments, seg_offsets,
+                                                                                              chunk_off, cand, cap_cand);
     refine_kernel<<<592, 128, 0, st>>>(P, ep, cand, counters, cap_cand, ext_tmp, keep);
     launches += 2;
     launches += exclusive_scan(keep, keep_off, chunk_off, 0, &counters->n_cand, cap_cand,

@@ -500,13 +500,15 @@ namespace sb {
       for (int j = 0; j <= S::c; ++j)
         prm.taps[j] = taps.v[j];
 
-      // Segments: as many CTAs as the machine holds at once (148 SMs x 2 resident CTAs), no more:
-      // every segment pays 2c warm-up rows, so a second wave only adds overhead.  Small layers
-      // keep segments of at least 32 output rows.
+      // Segments.  Every segment pays 2c warm-up rows and works in 32-row blocks.  A large layer
+      // is cut into as many CTAs as the machine holds at once (148 SMs x 2 resident CTAs) and no
+      // more -- a second wave would only add warm-up rows.  A small layer cannot fill the machine;
+      // there the launch is latency bound (a CTA walks its blocks one after the other), so it gets
+      // short segments of 64 - 2c output rows: exactly two blocks each.
       const int n_strips = (w + TX - 1) / TX;
       const int slots = 148 * per_sm;
-      int best_segs = std::max(1, slots / n_strips);
-      best_segs = std::min(best_segs, std::max(1, h / 32));
+      const int hy_short = 2 * R - 2 * S::c;
+      int best_segs = std::max(1, std::min((h + hy_short - 1) / hy_short, slots / n_strips));
       static const int force = [] {
         const char* e = getenv("SARA_B200_MARCH_SEGS");
         return e ? atoi(e) : 0;

@@ -89,8 +89,11 @@ namespace sb {
     }
 
     // Small arrays (the usual case: row counters, keep flags, orientation counts): one block,
-    // one launch.  Thread t owns the slice [t m, (t + 1) m); final offsets go to out_off and the
-    // chunk offsets are zero, so consumers keep using out_off[i] + chunk_off[i >> 10].
+    // one launch.  The array is consumed in tiles of 16384 = 4 sub-tiles of 4096; thread t owns
+    // items 4t .. 4t + 3 of every sub-tile (16-byte coalesced loads, all four issued together), a
+    // running carry links sub-tiles and tiles.  Final offsets go to out_off and the chunk offsets
+    // are zero, so consumers keep using out_off[i] + chunk_off[i >> 10].  vals and out_off must be
+    // 16-byte aligned (they are: cudaMalloc'd arrays at 256-byte offsets).
     static __global__ void __launch_bounds__(1024)
         scan_single_kernel(const int* __restrict__ vals, int* __restrict__ out_off, int* __restrict__ chunk_off,
                            int n_static, const int* __restrict__ n_ptr, int n_cap, int* __restrict__ total_out,
@@ -98,25 +101,58 @@ namespace sb {
     {
       __shared__ int total;
       const int n = n_ptr ? min(*n_ptr, n_cap) : n_static;
-      const int m = (n + 1023) >> 10;
-      const int lo = min(static_cast<int>(threadIdx.x) * m, n), hi = min(lo + m, n);
-      int sum = 0;
-      for (int i = lo; i < hi; ++i)
-        sum += vals[i];
-      int run = block_exclusive_scan_1024(sum, &total);
-      for (int i = lo; i < hi; ++i)
+      const bool vec = ((reinterpret_cast<uintptr_t>(vals) | reinterpret_cast<uintptr_t>(out_off)) & 15) == 0;
+      int carry = 0;
+      for (int base = 0; base < n; base += 16384)
       {
-        const int v = vals[i];
-        out_off[i] = run;
-        run += v;
+        int4 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+        {
+          const int lo = base + 4096 * j + 4 * static_cast<int>(threadIdx.x);
+          if (vec && lo + 3 < n)
+            v[j] = *reinterpret_cast<const int4*>(vals + lo);
+          else
+          {
+            v[j].x = lo < n ? vals[lo] : 0;
+            v[j].y = lo + 1 < n ? vals[lo + 1] : 0;
+            v[j].z = lo + 2 < n ? vals[lo + 2] : 0;
+            v[j].w = lo + 3 < n ? vals[lo + 3] : 0;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+        {
+          const int lo = base + 4096 * j + 4 * static_cast<int>(threadIdx.x);
+          if (base + 4096 * j >= n)  // block-uniform
+            break;
+          const int sum = v[j].x + v[j].y + v[j].z + v[j].w;
+          const int run = carry + block_exclusive_scan_1024(sum, &total);
+          const int4 o = make_int4(run, run + v[j].x, run + v[j].x + v[j].y, run + v[j].x + v[j].y + v[j].z);
+          if (vec && lo + 3 < n)
+            *reinterpret_cast<int4*>(out_off + lo) = o;
+          else
+          {
+            if (lo < n)
+              out_off[lo] = o.x;
+            if (lo + 1 < n)
+              out_off[lo + 1] = o.y;
+            if (lo + 2 < n)
+              out_off[lo + 2] = o.z;
+            if (lo + 3 < n)
+              out_off[lo + 3] = o.w;
+          }
+          carry += total;
+          __syncthreads();
+        }
       }
       for (int c = threadIdx.x; c <= (n >> 10); c += 1024)
         chunk_off[c] = 0;
       if (threadIdx.x == 0)
       {
-        if (total > total_cap)
+        if (carry > total_cap)
           atomicOr(overflow, overflow_bit);
-        *total_out = total;  // the true count; consumers clamp to their capacity
+        *total_out = carry;  // the true count; consumers clamp to their capacity
       }
     }
 
