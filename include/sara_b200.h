@@ -261,6 +261,68 @@ SARA_B200_API int sara_b200_gaussian(sara_b200_ctx* ctx, const float* src, int w
  * (negative of the needed capacity if `capacity` is too small). */
 SARA_B200_API int sara_b200_make_gaussian_kernel(float sigma, float gauss_truncate, float* taps, int capacity);
 
+/* ---- descriptor matching: AnnMatcher (FeatureMatching/AnnMatcher.hpp:33-84,
+ * AnnMatcher.cpp:57-282) -------------------------------------------------------
+ * The reference builds two FLANN KD-tree forests (third-party/flann,
+ * KDTreeIndexParams{8}) and asks each descriptor for its 3 nearest neighbours in the
+ * other set -- an approximate search.  Here the search is EXACT (the answer of FLANN's
+ * LinearIndex, distances with the bits of flann::L2<float>, algorithms/dist.h:151-178):
+ * candidates come from a tcgen05 tensor-core pass over all pairs (dim == 128), are
+ * re-ranked in fp32 and certified; see sara_b200/csrc/match.cu. */
+typedef struct sara_b200_match
+{
+  int32_t x_index, y_index; /* Match::x_index(), y_index(): rows of keys1 / keys2 (Match/Match.hpp:100-113) */
+  int32_t rank;             /* Match::rank() */
+  float score;              /* Match::score(): ratio of SQUARED distances (AnnMatcher.cpp:135-158) */
+  int32_t direction;        /* Match::Direction: 0 SourceToTarget, 1 TargetToSource */
+} sara_b200_match;          /* 20 bytes */
+
+typedef struct sara_b200_match_args
+{
+  float sift_ratio_thres;          /* 1.2f (AnnMatcher.hpp:41); squared inside, as the reference does */
+  int32_t self_matching;           /* 0: AnnMatcher(keys1, keys2, ratio); 1: AnnMatcher(keys, ratio, metric, pixel) */
+  float min_max_metric_dist_thres; /* 0.5f, KeyProximity (FeatureMatching/KeyProximity.hpp:33) */
+  float pixel_dist_thres;          /* 10.f */
+  int32_t knn_mode;                /* SARA_B200_KNN_AUTO */
+} sara_b200_match_args;
+
+enum
+{
+  SARA_B200_KNN_AUTO = 0,   /* tensor cores when dim == 128 and the problem is not tiny */
+  SARA_B200_KNN_SCALAR = 1, /* exact fp32 CUDA-core search only */
+  SARA_B200_KNN_TENSOR = 2  /* tcgen05 candidates + exact re-ranking (dim must be 128) */
+};
+
+typedef struct sara_b200_knn_stats
+{
+  int32_t used_tensor_cores;
+  int32_t n_redone;  /* queries the certificate handed to the exact scalar kernel */
+  int32_t launches;
+  int32_t splits;
+  float gpu_ms;      /* CUDA events around the search, copies excluded */
+} sara_b200_knn_stats;
+
+SARA_B200_API void sara_b200_default_match_args(sara_b200_match_args* a);
+/* tree.knnSearch(query, indices, dists, k, SearchParams()) for every row of `queries` against
+ * `data` (both n x dim row-major floats; host pointers, or device pointers when `on_device`),
+ * k <= 8, dim <= 256.  idx / dist: nq x k on the host, ascending distance, equal distances by
+ * ascending index (KNNSimpleResultSet, util/result_set.h:151-171); unused entries are
+ * (-1, FLT_MAX).  stats may be NULL. */
+SARA_B200_API int sara_b200_knn(sara_b200_ctx* ctx, const float* queries, int nq, const float* data, int nd, int dim,
+                                int k, int on_device, int knn_mode, int32_t* idx, float* dist,
+                                sara_b200_knn_stats* stats);
+/* AnnMatcher::compute_matches().  desc1 / desc2: n x dim descriptors (KeypointList's
+ * Tensor_<float, 2>); kp1 / kp2: the matching features, needed for self matching (KeyProximity)
+ * and for Match::operator== on features, NULL otherwise (matches are then equal when their index
+ * pairs are).  For self matching pass the same arrays twice.  Matches are written to `out`
+ * (capacity entries) ordered by score; *n_out is the full count, OVERFLOW is returned when it
+ * exceeds `capacity`.  Empty key lists give BAD_ARG ("the list of key-points is empty",
+ * AnnMatcher.cpp:45-46). */
+SARA_B200_API int sara_b200_compute_matches(sara_b200_ctx* ctx, const float* desc1, const sara_b200_keypoint* kp1, int n1,
+                                  const float* desc2, const sara_b200_keypoint* kp2, int n2, int dim, int on_device,
+                                  const sara_b200_match_args* args, sara_b200_match* out, int capacity, int* n_out,
+                                  sara_b200_knn_stats* stats);
+
 #ifdef __cplusplus
 }
 #endif

@@ -37,8 +37,9 @@ KEYPOINT_DTYPE = np.dtype(
 def build(force: bool = False) -> str:
     """Compile the oracle with its Makefile (gcc only, no GPU)."""
     src = os.path.join(_HERE, "sift_oracle.cpp")
-    stale = (not os.path.exists(_LIB_PATH)) or (
-        os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(_LIB_PATH)
+    srcs = [src, os.path.join(_HERE, "match_oracle.cpp")]
+    stale = (not os.path.exists(_LIB_PATH)) or any(
+        os.path.exists(f) and os.path.getmtime(f) > os.path.getmtime(_LIB_PATH) for f in srcs
     )
     if force or stale:
         if not os.path.exists(src):

@@ -7,6 +7,9 @@ there is no CPU fallback (creation raises when the library or a device is
 missing).
 """
 from .api import (  # noqa: F401
+    AnnMatcher,
+    MATCH_DTYPE,
+    match,
     ComputeDoGExtrema,
     ImagePyramidParams,
     KEYPOINT_DTYPE,

@@ -66,6 +66,27 @@ class _DogArgs(C.Structure):
     ]
 
 
+class _MatchArgs(C.Structure):
+    _fields_ = [
+        ("sift_ratio_thres", C.c_float), ("self_matching", C.c_int32), ("min_max_metric_dist_thres", C.c_float),
+        ("pixel_dist_thres", C.c_float), ("knn_mode", C.c_int32),
+    ]
+
+
+class KnnStats(C.Structure):
+    _fields_ = [
+        ("used_tensor_cores", C.c_int32), ("n_redone", C.c_int32), ("launches", C.c_int32), ("splits", C.c_int32),
+        ("gpu_ms", C.c_float),
+    ]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+MATCH_DTYPE = np.dtype([("x_index", "<i4"), ("y_index", "<i4"), ("rank", "<i4"), ("score", "<f4"), ("direction", "<i4")])
+KNN_MODES = {"auto": 0, "scalar": 1, "tensor": 2}
+
+
 class Timings(C.Structure):
     _fields_ = [
         ("upload", C.c_float), ("pyramid", C.c_float), ("extrema", C.c_float),
@@ -91,6 +112,7 @@ SYMBOLS = [
     "sara_b200_copy_extrema", "sara_b200_copy_oriented", "sara_b200_gaussian",
     "sara_b200_make_gaussian_kernel", "sara_b200_sift_u8", "sara_b200_sift_enqueue_u8", "sara_b200_to_gray32f",
     "sara_b200_collect_device", "sara_b200_set_graphs",
+    "sara_b200_default_match_args", "sara_b200_knn", "sara_b200_compute_matches",
 ]
 
 
@@ -149,6 +171,12 @@ def load_library() -> C.CDLL:
     L.sara_b200_default_pyramid_params.argtypes = [C.POINTER(_PyrParams)]
     L.sara_b200_default_sift_args.argtypes = [C.POINTER(_SiftArgs)]
     L.sara_b200_default_dog_args.argtypes = [C.POINTER(_DogArgs)]
+    L.sara_b200_default_match_args.argtypes = [C.POINTER(_MatchArgs)]
+    L.sara_b200_default_match_args.restype = None
+    L.sara_b200_knn.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp,
+                                C.POINTER(KnnStats)]
+    L.sara_b200_compute_matches.argtypes = [vp, vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int,
+                                            C.POINTER(_MatchArgs), vp, C.c_int, ip, C.POINTER(KnnStats)]
     _LIB = L
     return L
 
@@ -261,6 +289,61 @@ class SiftContext:
     def _check(self, rc):
         if rc != 0:
             _raise(self._L, self._ctx, rc)
+
+    # ---- descriptor matching (AnnMatcher) ----------------------------------------
+    @staticmethod
+    def _as_desc(d):
+        """(pointer, n, dim, on_device, keepalive) of an n x dim float32 matrix (numpy or torch)."""
+        if hasattr(d, "data_ptr"):
+            if d.dim() != 2 or str(d.dtype) != "torch.float32" or not d.is_contiguous():
+                raise ValueError("descriptor tensor must be 2-D contiguous float32")
+            return d.data_ptr(), int(d.shape[0]), int(d.shape[1]), bool(d.is_cuda), d
+        a = np.ascontiguousarray(d, dtype=np.float32)
+        if a.ndim != 2:
+            raise ValueError("descriptors must be an n x dim float32 matrix")
+        return a.ctypes.data, int(a.shape[0]), int(a.shape[1]), False, a
+
+    def knn(self, queries, data, k: int = 3, mode="auto"):
+        """flann::Index::knnSearch for every query row, exact (see include/sara_b200.h).
+        Returns (idx (nq, k) int32, dist (nq, k) float32, stats dict)."""
+        qp, nq, dim, q_dev, qk = self._as_desc(queries)
+        dp, nd, dim2, d_dev, dk = self._as_desc(data)
+        if dim != dim2 or q_dev != d_dev:
+            raise ValueError("queries and data must have the same dimension and live on the same side")
+        idx = np.empty((nq, k), np.int32)
+        dist = np.empty((nq, k), np.float32)
+        st = KnnStats()
+        self._check(self._L.sara_b200_knn(self._ctx, qp, nq, dp, nd, dim, k, int(q_dev), KNN_MODES.get(mode, mode),
+                                          idx.ctypes.data, dist.ctypes.data, C.byref(st)))
+        return idx, dist, st.asdict()
+
+    def compute_matches(self, desc1, desc2, sift_ratio_thres: float = 1.2, feat1=None, feat2=None,
+                        self_matching: bool = False, min_max_metric_dist_thres: float = 0.5,
+                        pixel_dist_thres: float = 10.0, mode="auto", return_stats: bool = False):
+        """AnnMatcher(keys1, keys2, sift_ratio_thres).compute_matches() (AnnMatcher.cpp:219-282)."""
+        p1, n1, dim, dev1, k1 = self._as_desc(desc1)
+        p2, n2, dim2, dev2, k2 = self._as_desc(desc2)
+        if n1 and n2 and (dim != dim2 or dev1 != dev2):
+            raise ValueError("the two descriptor matrices must have the same dimension and live on the same side")
+        f1 = np.ascontiguousarray(feat1, dtype=KEYPOINT_DTYPE) if feat1 is not None else None
+        f2 = np.ascontiguousarray(feat2, dtype=KEYPOINT_DTYPE) if feat2 is not None else None
+        args = _MatchArgs(sift_ratio_thres, int(self_matching), min_max_metric_dist_thres, pixel_dist_thres,
+                          KNN_MODES.get(mode, mode))
+        cap = max(4 * (n1 + n2), 1024)
+        st = KnnStats()
+        while True:
+            out = np.empty(cap, MATCH_DTYPE)
+            n = C.c_int(0)
+            rc = self._L.sara_b200_compute_matches(self._ctx, p1, f1.ctypes.data if f1 is not None else None, n1, p2,
+                                                   f2.ctypes.data if f2 is not None else None, n2, max(dim, 1),
+                                                   int(dev1), C.byref(args), out.ctypes.data, cap, C.byref(n),
+                                                   C.byref(st))
+            if rc == -5 and n.value > cap:  # OVERFLOW: the full count came back
+                cap = n.value
+                continue
+            self._check(rc)
+            res = out[: n.value].copy()
+            return (res, st.asdict()) if return_stats else res
 
     # ---- compute_sift_keypoints ------------------------------------------------
     @staticmethod
@@ -513,3 +596,44 @@ def compute_sift_keypoints(image, pyramid_params: ImagePyramidParams | None = No
     # `keep` is the converted array / tensor: handed on as is, no second conversion
     return ctx.compute_sift_keypoints(keep, pyramid_params, gauss_truncate, extremum_thres, edge_ratio_thres,
                                       extremum_refinement_iter)
+
+
+class AnnMatcher:
+    """DO::Sara::AnnMatcher (FeatureMatching/AnnMatcher.hpp:33-84): same constructors, `compute_matches()`
+    returns the matches ordered by score as a MATCH_DTYPE array (Match::x_index, y_index, rank, score,
+    matching_direction).  The search is exact (FLANN's LinearIndex answer), not the reference's KD-tree forest."""
+
+    def __init__(self, keys1: KeypointList, keys2: KeypointList | float | None = None, sift_ratio_thres: float = 1.2,
+                 min_max_metric_dist_thres: float = 0.5, pixel_dist_thres: float = 10.0, ctx: SiftContext | None = None,
+                 device: int = 0):
+        if keys2 is None or isinstance(keys2, (int, float)):  # AnnMatcher(keys, ratio, metric, pixel): self matching
+            if isinstance(keys2, (int, float)):
+                sift_ratio_thres = float(keys2)
+            keys2, self._self = keys1, True
+        else:
+            self._self = False
+        for k in (keys1, keys2):  # size_consistency_predicate (Features/KeypointList.hpp)
+            if len(k.features) != len(k.descriptors):
+                raise RuntimeError("The list of keypoints are inconsistent in size!")
+        self.keys1, self.keys2 = keys1, keys2
+        self.sift_ratio_thres = sift_ratio_thres
+        self.metric, self.pixel = min_max_metric_dist_thres, pixel_dist_thres
+        self._ctx, self._device = ctx, device
+
+    def compute_matches(self, mode="auto") -> np.ndarray:
+        ctx = self._ctx
+        if ctx is None:
+            ctx = _DEFAULT_CTX.get(self._device)
+            if ctx is None:
+                ctx = SiftContext(64, 64, self._device)
+                ctx._w, ctx._h = 64, 64
+                _DEFAULT_CTX[self._device] = ctx
+        return ctx.compute_matches(self.keys1.descriptors, self.keys2.descriptors, self.sift_ratio_thres,
+                                   self.keys1.features, self.keys2.features, self._self, self.metric, self.pixel, mode)
+
+    compute_self_matches = compute_matches
+
+
+def match(keys1: KeypointList, keys2: KeypointList, lowe_ratio: float = 0.6) -> np.ndarray:
+    """DO::Sara::match (SfM/Helpers/KeypointMatching.cpp:19-25)."""
+    return AnnMatcher(keys1, keys2, lowe_ratio).compute_matches()

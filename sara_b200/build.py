@@ -15,8 +15,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsara_b200.so")
-SOURCES = ["ctx.cu", "ingest.cu", "pyramid.cu", "pyramid_fused.cu", "pyramid_stage.cu", "pyramid_march.cu", "extrema.cu", "describe.cu"]
-HEADERS = ["common.cuh", "scan.cuh", "fp32x2_tma.cuh", os.path.join("..", "..", "include", "sara_b200.h")]
+SOURCES = ["ctx.cu", "match.cu", "ingest.cu", "pyramid.cu", "pyramid_fused.cu", "pyramid_stage.cu", "pyramid_march.cu", "extrema.cu", "describe.cu"]
+HEADERS = ["common.cuh", "match.cuh", "scan.cuh", "fp32x2_tma.cuh", os.path.join("..", "..", "include", "sara_b200.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "match.cuh"
 
 using namespace sb;
 
@@ -102,6 +103,9 @@ struct sara_b200_ctx
   double* d_gray_lut = nullptr;   // 3 x 256 products of the rgb -> gray conversion (ingest.cu)
   float* scratch = nullptr;       // sara_b200_gaussian / sara_b200_to_gray32f work buffers (grown on demand)
   size_t scratch_bytes = 0;
+  sb::match::Workspace match_ws;  // nearest-neighbour search (match.cu)
+  unsigned char* match_io = nullptr;  // device copies of host descriptors + result buffers of the matcher
+  size_t match_io_bytes = 0;
   char err[512] = "";
 };
 
@@ -929,6 +933,8 @@ void sara_b200_destroy(sara_b200_ctx* ctx)
   }
   cudaFree(ctx->d_gray_lut);
   cudaFree(ctx->scratch);
+  cudaFree(ctx->match_io);
+  ctx->match_ws.release();
   delete ctx;
 }
 
@@ -1490,3 +1496,352 @@ int sara_b200_make_gaussian_kernel(float sigma, float gauss_truncate, float* tap
 }
 
 }  // extern "C"
+
+// ---- descriptor matching: AnnMatcher over the device search of match.cu ------
+namespace {
+
+  int grow_match_io(sara_b200_ctx* ctx, size_t bytes)
+  {
+    if (bytes <= ctx->match_io_bytes)
+      return 0;
+    if (ctx->match_io)
+    {
+      CU(ctx, cudaStreamSynchronize(ctx->slots[0].own_stream));
+      CU(ctx, cudaFree(ctx->match_io));
+      ctx->match_io = nullptr;
+      ctx->match_io_bytes = 0;
+    }
+    CU(ctx, cudaMalloc(&ctx->match_io, bytes));
+    ctx->match_io_bytes = bytes;
+    return 0;
+  }
+
+  struct KnnResult
+  {
+    std::vector<int32_t> idx;
+    std::vector<float> dist;
+  };
+
+  // One search, device pointers in, host vectors out (k entries per query).
+  int knn_to_host(sara_b200_ctx* ctx, const float* d_q, int nq, const float* d_data, int nd, int dim, int k, int mode,
+                  int32_t* d_idx, float* d_dist, int32_t* h_idx, float* h_dist, sara_b200_knn_stats* stats,
+                  cudaStream_t st)
+  {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (stats)
+    {
+      CU(ctx, cudaEventCreate(&e0));
+      CU(ctx, cudaEventCreate(&e1));
+      CU(ctx, cudaEventRecord(e0, st));
+    }
+    sb::match::KnnStats ks;
+    const int rc = sb::match::knn(ctx->match_ws, d_q, nq, d_data, nd, dim, k, mode, d_idx, d_dist, &ks, st, ctx->err,
+                                  sizeof ctx->err);
+    if (rc)
+      return rc;
+    if (stats)
+      CU(ctx, cudaEventRecord(e1, st));
+    CU(ctx, cudaMemcpyAsync(h_idx, d_idx, sizeof(int32_t) * nq * k, cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaMemcpyAsync(h_dist, d_dist, sizeof(float) * nq * k, cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    if (stats)
+    {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, e0, e1);
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+      stats->used_tensor_cores |= ks.used_tensor_cores;
+      stats->n_redone += ks.n_redone;
+      stats->launches += ks.launches;
+      stats->splits = ks.splits;
+      stats->gpu_ms += ms;
+    }
+    return 0;
+  }
+
+  template <class T>
+  T* carve_io(unsigned char*& cur, size_t n)
+  {
+    T* p = reinterpret_cast<T*>(cur);
+    cur += align_up(n * sizeof(T), 256);
+    return p;
+  }
+
+}  // namespace
+
+void sara_b200_default_match_args(sara_b200_match_args* a)
+{
+  if (!a)
+    return;
+  a->sift_ratio_thres = 1.2f;  // AnnMatcher.hpp:41
+  a->self_matching = 0;
+  a->min_max_metric_dist_thres = 0.5f;  // AnnMatcher.hpp:45-46
+  a->pixel_dist_thres = 10.f;
+  a->knn_mode = SARA_B200_KNN_AUTO;
+}
+
+int sara_b200_knn(sara_b200_ctx* ctx, const float* queries, int nq, const float* data, int nd, int dim, int k,
+                  int on_device, int knn_mode, int32_t* idx, float* dist, sara_b200_knn_stats* stats)
+{
+  if (!ctx)
+    return fail(nullptr, SARA_B200_ERR_BAD_ARG, "null context");
+  if (!queries || !data || !idx || !dist || nq < 0 || nd < 0 || dim < 1 || k < 1)
+    return fail(ctx, SARA_B200_ERR_BAD_ARG, "knn: bad arguments");
+  if (stats)
+    memset(stats, 0, sizeof *stats);
+  if (nq == 0)
+    return 0;
+  DeviceGuard guard(ctx->device);
+  CU(ctx, guard.err);
+  cudaStream_t st = ctx->slots[0].own_stream;
+  const size_t qb = sizeof(float) * nq * dim, db = sizeof(float) * nd * dim;
+  int rc = grow_match_io(ctx, (on_device ? 0 : align_up(qb, 256) + align_up(db, 256)) + 2 * align_up(sizeof(float) * nq * k, 256));
+  if (rc)
+    return rc;
+  unsigned char* cur = ctx->match_io;
+  const float* d_q = queries;
+  const float* d_d = data;
+  if (!on_device)
+  {
+    float* q = carve_io<float>(cur, static_cast<size_t>(nq) * dim);
+    float* d = carve_io<float>(cur, static_cast<size_t>(nd) * dim);
+    CU(ctx, cudaMemcpyAsync(q, queries, qb, cudaMemcpyHostToDevice, st));
+    if (nd)
+      CU(ctx, cudaMemcpyAsync(d, data, db, cudaMemcpyHostToDevice, st));
+    d_q = q;
+    d_d = d;
+  }
+  int32_t* d_idx = carve_io<int32_t>(cur, static_cast<size_t>(nq) * k);
+  float* d_dist = carve_io<float>(cur, static_cast<size_t>(nq) * k);
+  return knn_to_host(ctx, d_q, nq, d_d, nd, dim, k, knn_mode, d_idx, d_dist, idx, dist, stats, st);
+}
+
+int sara_b200_compute_matches(sara_b200_ctx* ctx, const float* desc1, const sara_b200_keypoint* kp1, int n1, const float* desc2,
+                    const sara_b200_keypoint* kp2, int n2, int dim, int on_device, const sara_b200_match_args* args,
+                    sara_b200_match* out, int capacity, int* n_out, sara_b200_knn_stats* stats)
+{
+  if (!ctx)
+    return fail(nullptr, SARA_B200_ERR_BAD_ARG, "null context");
+  if (!args || !n_out || capacity < 0 || (capacity > 0 && !out) || n1 < 0 || n2 < 0 || dim < 1)
+    return fail(ctx, SARA_B200_ERR_BAD_ARG, "match: bad arguments");
+  *n_out = 0;
+  if (stats)
+    memset(stats, 0, sizeof *stats);
+  if (n1 == 0 || n2 == 0 || !desc1 || !desc2)
+    return fail(ctx, SARA_B200_ERR_BAD_ARG, "Error: the list of key-points is empty!");  // AnnMatcher.cpp:45-46
+  const bool self = args->self_matching != 0;
+  if (self && (!kp1 || !kp2))
+    return fail(ctx, SARA_B200_ERR_BAD_ARG, "match: self matching needs the features (KeyProximity)");
+  DeviceGuard guard(ctx->device);
+  CU(ctx, guard.err);
+  cudaStream_t st = ctx->slots[0].own_stream;
+
+  const float sq_thres = args->sift_ratio_thres * args->sift_ratio_thres;
+  const float sq_metric = args->min_max_metric_dist_thres * args->min_max_metric_dist_thres;
+  const float sq_pixel = args->pixel_dist_thres * args->pixel_dist_thres;
+  const int K = 3;
+
+  // device staging: descriptors (when they come from the host), k-NN outputs, radii / counts / offsets
+  const size_t b1 = sizeof(float) * n1 * dim, b2 = sizeof(float) * n2 * dim;
+  const int nmax = std::max(n1, n2);
+  size_t need = (on_device ? 0 : align_up(b1, 256) + align_up(b2, 256)) + 2 * align_up(sizeof(float) * nmax * K, 256) +
+                3 * align_up(sizeof(float) * nmax, 256);
+  int rc = grow_match_io(ctx, need);
+  if (rc)
+    return rc;
+  unsigned char* cur = ctx->match_io;
+  const float* d1 = desc1;
+  const float* d2 = desc2;
+  if (!on_device)
+  {
+    float* p1 = carve_io<float>(cur, static_cast<size_t>(n1) * dim);
+    float* p2 = carve_io<float>(cur, static_cast<size_t>(n2) * dim);
+    CU(ctx, cudaMemcpyAsync(p1, desc1, b1, cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaMemcpyAsync(p2, desc2, b2, cudaMemcpyHostToDevice, st));
+    d1 = p1;
+    d2 = p2;
+  }
+  int32_t* d_idx = carve_io<int32_t>(cur, static_cast<size_t>(nmax) * K);
+  float* d_dist = carve_io<float>(cur, static_cast<size_t>(nmax) * K);
+  float* d_radius = carve_io<float>(cur, nmax);
+  int* d_count = carve_io<int>(cur, nmax);
+  int* d_off = carve_io<int>(cur, nmax);
+
+  struct Side
+  {
+    const float* d;
+    const sara_b200_keypoint* kp;
+    int n;
+  };
+  const Side sides[2] = {{d1, kp1, n1}, {d2, kp2, n2}};
+  std::vector<sara_b200_match> matches;
+  matches.reserve(100000);
+
+  auto squared_ref_distance = [](const float* M, float ax, float ay, float bx, float by) {  // Metric.hpp:46-49
+    const float dx = bx - ax, dy = by - ay;
+    const float mx = M[0] * dx + M[2] * dy, my = M[1] * dx + M[3] * dy;
+    return dx * mx + dy * my;
+  };
+  auto is_redundant = [&](const sara_b200_keypoint& f1, const sara_b200_keypoint& f2) {  // KeyProximity.cpp:17-30
+    const float sd1 = squared_ref_distance(f1.shape, f1.x, f1.y, f2.x, f2.y);
+    const float sd2 = squared_ref_distance(f2.shape, f1.x, f1.y, f2.x, f2.y);
+    const float dx = f1.x - f2.x, dy = f1.y - f2.y;
+    return dx * dx + dy * dy < sq_pixel || sd1 < sq_metric || sd2 < sq_metric;
+  };
+
+  // both directions of AnnMatcher.cpp:242-254; `one` queries, `two` is the indexed set
+  for (int dir = 0; dir < 2; ++dir)
+  {
+    const Side& one = sides[dir];
+    const Side& two = sides[1 - dir];
+    auto push = [&](int i1, int i2, float score, int rank) {
+      sara_b200_match m;
+      m.x_index = dir == 0 ? i1 : i2;
+      m.y_index = dir == 0 ? i2 : i1;
+      m.rank = rank;
+      m.score = score;
+      m.direction = dir;
+      matches.push_back(m);
+    };
+    if (two.n == 1 && !self)  // boundary case 2 (AnnMatcher.cpp:88-103)
+    {
+      if (1.f < sq_thres)
+        for (int i1 = 0; i1 < one.n; ++i1)
+          push(i1, 0, 1.f, 1);
+      continue;
+    }
+    std::vector<int32_t> idx(static_cast<size_t>(one.n) * K);
+    std::vector<float> dist(static_cast<size_t>(one.n) * K);
+    rc = knn_to_host(ctx, one.d, one.n, two.d, two.n, dim, K, args->knn_mode, d_idx, d_dist, idx.data(), dist.data(),
+                     stats, st);
+    if (rc)
+      return rc;
+    if (two.n == 2 && self)  // boundary case 3 (AnnMatcher.cpp:106-125)
+    {
+      if (1.f < sq_thres)
+        for (int i1 = 0; i1 < one.n; ++i1)
+          push(i1, idx[static_cast<size_t>(i1) * K + 1], 1.f, 1);
+      continue;
+    }
+    const int top1 = self ? 1 : 0;
+
+    // adaptive radius search (AnnMatcher.cpp:139-146): every neighbour with dist < d(top1) * ratio^2
+    std::vector<int> r_off, r_idx;
+    std::vector<float> r_dist;
+    if (sq_thres > 1.f)
+    {
+      std::vector<float> radius(one.n);
+      for (int i1 = 0; i1 < one.n; ++i1)
+        radius[i1] = dist[static_cast<size_t>(i1) * K + top1] * sq_thres;
+      CU(ctx, cudaMemcpyAsync(d_radius, radius.data(), sizeof(float) * one.n, cudaMemcpyHostToDevice, st));
+      rc = sb::match::radius_pass(one.d, one.n, two.d, two.n, dim, d_radius, d_count, nullptr, nullptr, nullptr, st,
+                                  ctx->err, sizeof ctx->err);
+      if (rc)
+        return rc;
+      std::vector<int> count(one.n);
+      CU(ctx, cudaMemcpyAsync(count.data(), d_count, sizeof(int) * one.n, cudaMemcpyDeviceToHost, st));
+      CU(ctx, cudaStreamSynchronize(st));
+      r_off.assign(one.n + 1, 0);
+      size_t total = 0;
+      for (int i1 = 0; i1 < one.n; ++i1)
+      {
+        r_off[i1] = static_cast<int>(total);
+        total += count[i1];
+        if (total > (size_t(1) << 27))
+          return fail(ctx, SARA_B200_ERR_OVERFLOW, "match: more than 2^27 neighbours inside the adaptive radii");
+      }
+      r_off[one.n] = static_cast<int>(total);
+      r_idx.resize(total);
+      r_dist.resize(total);
+      if (total)
+      {
+        int* d_ridx = nullptr;
+        float* d_rdist = nullptr;
+        CU(ctx, cudaMalloc(&d_ridx, sizeof(int) * total));
+        if (cudaMalloc(&d_rdist, sizeof(float) * total) != cudaSuccess)
+        {
+          cudaFree(d_ridx);
+          return fail(ctx, SARA_B200_ERR_OOM, "match: cudaMalloc of the radius results failed");
+        }
+        cudaMemcpyAsync(d_off, r_off.data(), sizeof(int) * one.n, cudaMemcpyHostToDevice, st);
+        rc = sb::match::radius_pass(one.d, one.n, two.d, two.n, dim, d_radius, d_count, d_off, d_ridx, d_rdist, st,
+                                    ctx->err, sizeof ctx->err);
+        cudaMemcpyAsync(r_idx.data(), d_ridx, sizeof(int) * total, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(r_dist.data(), d_rdist, sizeof(float) * total, cudaMemcpyDeviceToHost, st);
+        const cudaError_t e = cudaStreamSynchronize(st);
+        cudaFree(d_ridx);
+        cudaFree(d_rdist);
+        if (rc)
+          return rc;
+        if (e != cudaSuccess)
+          return fail(ctx, SARA_B200_ERR_CUDA, "match: radius search failed: %s", cudaGetErrorString(e));
+      }
+    }
+
+    std::vector<std::pair<float, int>> seg;
+    for (int i1 = 0; i1 < one.n; ++i1)
+    {
+      const int32_t* I = idx.data() + static_cast<size_t>(i1) * K;
+      const float* D = dist.data() + static_cast<size_t>(i1) * K;
+      const float top1_score = D[top1 + 1] > 0.f ? D[top1] / D[top1 + 1] : 0.f;
+      if (!(sq_thres > 1.f))
+      {
+        // K = 1: the loop of AnnMatcher.cpp:149-170 runs for rank = top1 < 1 only, i.e. never when
+        // self matching (top1 = 1): self matches exist only on the radius branch.
+        if (top1 != 0 || top1_score > sq_thres)
+          continue;
+        push(i1, I[0], top1_score, 1);
+        continue;
+      }
+      // RadiusResultSet::copy(sorted): by (dist, index)
+      seg.clear();
+      for (int e = r_off[i1]; e < r_off[i1 + 1]; ++e)
+        seg.emplace_back(r_dist[e], r_idx[e]);
+      std::sort(seg.begin(), seg.end());
+      const int Kn = static_cast<int>(seg.size());
+      for (int rank = top1; rank < Kn; ++rank)
+      {
+        float score = 0.f;
+        if (rank == top1)
+          score = top1_score;
+        else if (seg[top1].first)
+          score = seg[rank].first / seg[top1].first;
+        if (score > sq_thres)
+          break;
+        const int i2 = seg[rank].second;
+        if (self && is_redundant(one.kp[i1], two.kp[i2]))
+          continue;
+        push(i1, i2, score, top1 == 0 ? rank + 1 : rank);
+      }
+    }
+  }
+
+  // AnnMatcher.cpp:256-276: lexicographic sort, unique, sort by score (ties keep the lexicographic order)
+  std::sort(matches.begin(), matches.end(), [](const sara_b200_match& a, const sara_b200_match& b) {
+    if (a.x_index != b.x_index)
+      return a.x_index < b.x_index;
+    if (a.y_index != b.y_index)
+      return a.y_index < b.y_index;
+    return a.score < b.score;
+  });
+  auto same_feature = [](const sara_b200_keypoint& a, const sara_b200_keypoint& b) {  // Feature.hpp:140-146
+    return a.x == b.x && a.y == b.y && a.shape[0] == b.shape[0] && a.shape[1] == b.shape[1] && a.shape[2] == b.shape[2] &&
+           a.shape[3] == b.shape[3] && a.orientation == b.orientation && a.type == b.type;
+  };
+  auto equal = [&](const sara_b200_match& a, const sara_b200_match& b) {  // Match.hpp:159-162
+    if (kp1 && kp2)
+      return same_feature(kp1[a.x_index], kp1[b.x_index]) && same_feature(kp2[a.y_index], kp2[b.y_index]);
+    return a.x_index == b.x_index && a.y_index == b.y_index;
+  };
+  matches.resize(std::unique(matches.begin(), matches.end(), equal) - matches.begin());
+  std::stable_sort(matches.begin(), matches.end(),
+                   [](const sara_b200_match& a, const sara_b200_match& b) { return a.score < b.score; });
+
+  *n_out = static_cast<int>(matches.size());
+  const int n_copy = std::min<int>(*n_out, capacity);
+  if (n_copy)
+    memcpy(out, matches.data(), sizeof(sara_b200_match) * n_copy);
+  if (*n_out > capacity)
+    return fail(ctx, SARA_B200_ERR_OVERFLOW, "match: %d matches, capacity %d", *n_out, capacity);
+  return 0;
+}

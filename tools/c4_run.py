@@ -68,7 +68,9 @@ def sync():
     torch.cuda.synchronize(dev)
 
 
-extract(mine[:NS])  # warm-up
+warm = extract(mine[:NS])  # warm-up: kernels, and the NCCL communicator / its first connections
+if world > 1:
+    P.gather_keypoint_tensors(warm, dst=0)
 sync()
 e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
 e0.record()
