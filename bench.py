@@ -430,12 +430,78 @@ def run_ours(args):
                     "algorithmic_bytes": top_mb * 1e6, "ms": top_mean, "peak_source": peak_src,
                     "note": "bit-exact reference arithmetic (separate fp32 multiply and add per tap) makes the pyramid "
                             "fp32-pipe bound, not HBM bound: DESIGN.md section 3",
+                    "fp32_pipe": None,
                     "pyramid": {"achieved": algo / (mean_ms * 1e-3) / 1e9, "frac": algo / (mean_ms * 1e-3) / 1e9 / peak,
                                 "algorithmic_bytes": algo, "ms": mean_ms, "launches": t0["pyramid_launches"],
                                 "bytes_per_octave_pixel": ALGO_BYTES_PER_OCTAVE_PIXEL,
                                 "how": "CUDA events around the pyramid stage of single frames (one frame in flight, "
                                        "octaves overlapped on side streams), mean of 10"}}
         stage_ms = {k: float(np.mean(v)) for k, v in stage_acc.items()}
+        if top_mean:
+            # what actually bounds that launch: un-fused fp32 multiplies and adds.  Per pixel and
+            # pass the contract needs K additions and c + 1 multiplies (symmetric taps share their products).
+            K, c = 25, 12
+            lane_ops = 2.0 * (K + c + 1) * (top_mb * 1e6 / 12.0)
+            sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+            pipe_peak = 148 * 128 * sm_mhz * 1e6
+            roofline["fp32_pipe"] = {"achieved_lane_ops_per_s": lane_ops / (top_mean * 1e-3), "peak_lane_ops_per_s": pipe_peak,
+                                     "frac": lane_ops / (top_mean * 1e-3) / pipe_peak,
+                                     "how": "2 passes x (25 adds + 13 multiplies) per pixel of the launch / its duration, against "
+                                            "148 SMs x 128 fp32 lanes x the SM clock sampled during the run (no FMA: 1 op per lane-clock)"}
+
+    # ---- matching row: AnnMatcher between two frames of the batch, N = 1 view -------------
+    matching = None
+    if rank == 0:
+        try:
+            # a frame and the same scene moved by (3, 2) pixels with fresh sensor noise
+            moved = np.roll(frames[0], (2, 3), axis=(0, 1)) + np.random.default_rng(7).normal(0, 0.01, frames[0].shape)
+            d_pair = [d_frames[0], torch.from_numpy(np.clip(moved, 0, 1).astype(np.float32)).to(dev)]
+            kl = []
+            for i in (0, 1):
+                ctx.enqueue_raw(0, d_pair[i].data_ptr(), W4K, H4K, True, sargs, streams[0].cuda_stream)
+                kl.append(ctx.collect(0))
+            g = [torch.from_numpy(k.descriptors).to(dev) for k in kl]
+            ms = []
+            for _ in range(6):
+                _, _, st = ctx.knn(g[0], g[1], 3, mode="tensor")
+                ms.append(st["gpu_ms"])
+            knn_ms = float(np.median(ms[1:]))
+            t = []
+            for _ in range(5):
+                t0 = time.perf_counter()
+                m = ctx.compute_matches(g[0], g[1], 0.6, kl[0].features, kl[1].features)
+                t.append(time.perf_counter() - t0)
+            n1, n2 = len(kl[0]), len(kl[1])
+            flops = 2.0 * n1 * n2 * 384
+            bf16_peak = None
+            try:
+                bf16_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+            except Exception:
+                pass
+            matching = {"n1": n1, "n2": n2, "knn3_gpu_ms": knn_ms, "stats": st,
+                        "ann_match_0.6": {"wall_ms": 1e3 * float(np.median(t[1:])), "matches": int(len(m)),
+                                          "input": "descriptors resident on the device, both directions, match list to the host"},
+                        "tensor": {"bound": "tensor", "achieved": flops / (knn_ms * 1e-3) / 1e12, "peak": bf16_peak,
+                                   "unit": "TFLOP/s", "frac": (flops / (knn_ms * 1e-3) / 1e12 / bf16_peak) if bf16_peak else None,
+                                   "how": "2 n1 n2 x 384 (bf16 split: hi.hi + lo.hi + hi.lo) / the WHOLE search (split, tcgen05 "
+                                          "candidates, selection, exact re-ranking), CUDA events inside the library"}}
+            if cpu_baseline is not None and cpu_baseline.get("value"):
+                from oracle import match as OM
+
+                t0 = time.perf_counter()
+                i0, d0 = OM.knn_linear(kl[1].descriptors, kl[0].descriptors, 3)
+                matching["cpu_exact_knn3_ms"] = 1e3 * (time.perf_counter() - t0)
+                idx, dist, _ = ctx.knn(g[0], g[1], 3, mode="tensor")
+                matching["gpu_equals_cpu_exact"] = bool(np.array_equal(idx, i0) and
+                                                        np.array_equal(dist.view(np.uint32), d0.view(np.uint32)))
+                if OM.have_ref():
+                    t0 = time.perf_counter()
+                    kd = OM.FlannRef(kl[1].descriptors, "kdtree")
+                    ik, _ = kd.knn(kl[0].descriptors, 3)
+                    matching["reference_flann_kdtree_ms"] = 1e3 * (time.perf_counter() - t0)
+                    matching["reference_flann_kdtree_recall_nn"] = float((ik[:, 0] == i0[:, 0]).mean())
+        except Exception as e:
+            matching = {"unavailable": repr(e)}
 
     n_oct_all = ctx.num_octaves(0)
     if rank == 0:
@@ -454,7 +520,7 @@ def run_ours(args):
             "gpu_launches_per_frame": int(launches_per_frame),
             "host_enqueue_us_per_frame": host_enqueue_us,
             "clocks": clocks, "roofline": roofline, "stage_ms_per_frame": stage_ms, "cpu_baseline": cpu_baseline,
-            "timed_region_s": max_secs, "wall_s": wall,
+            "matching": matching, "timed_region_s": max_secs, "wall_s": wall,
         }
         print(json.dumps(line), flush=True)
     ctx.close()

@@ -301,6 +301,155 @@ namespace sara_b200 {
                            [](int n, int d) { return DescriptorMatrix{n, d}; });
   }
 
+  // ---- Match + AnnMatcher (Match/Match.hpp:27-177, FeatureMatching/AnnMatcher.hpp:33-84) ---- //
+  class Match
+  {
+  public:
+    enum class Direction : std::uint8_t
+    {
+      SourceToTarget,
+      TargetToSource
+    };
+    Match() = default;
+    Match(const OERegion* x, const OERegion* y, float score = std::numeric_limits<float>::max(),
+          Direction matching_dir = Direction::SourceToTarget, int x_index = -1, int y_index = -1)
+      : _x{x}, _y{y}, _x_index{x_index}, _y_index{y_index}, _score{score}, _matching_dir{matching_dir}
+    {
+    }
+    const OERegion* x_pointer() const { return _x; }
+    const OERegion* y_pointer() const { return _y; }
+    const OERegion& x() const
+    {
+      if (_x == nullptr)
+        throw std::runtime_error{"x is null"};
+      return *_x;
+    }
+    const OERegion& y() const
+    {
+      if (_y == nullptr)
+        throw std::runtime_error{"y is null"};
+      return *_y;
+    }
+    const Point2f& x_pos() const { return x().center(); }
+    const Point2f& y_pos() const { return y().center(); }
+    int rank() const { return _rank; }
+    int& rank() { return _rank; }
+    float score() const { return _score; }
+    Direction matching_direction() const { return _matching_dir; }
+    int x_index() const { return _x_index; }
+    int y_index() const { return _y_index; }
+
+  private:
+    const OERegion* _x = nullptr;
+    const OERegion* _y = nullptr;
+    int _x_index = -1, _y_index = -1, _rank = -1;
+    float _score = std::numeric_limits<float>::max();
+    Direction _matching_dir = Direction::SourceToTarget;
+  };
+
+  inline sara_b200_keypoint to_c_keypoint(const OERegion& r)
+  {
+    sara_b200_keypoint k{};
+    k.x = r.coords(0);
+    k.y = r.coords(1);
+    k.shape[0] = r.shape_matrix(0, 0);
+    k.shape[1] = r.shape_matrix(1, 0);
+    k.shape[2] = r.shape_matrix(0, 1);
+    k.shape[3] = r.shape_matrix(1, 1);
+    k.orientation = r.orientation;
+    k.extremum_value = r.extremum_value;
+    k.type = static_cast<std::uint8_t>(r.type);
+    k.extremum_type = static_cast<std::int8_t>(r.extremum_type);
+    return k;
+  }
+
+  //! Same constructors and compute_matches() as DO::Sara::AnnMatcher; the search underneath is the exact
+  //! one on the GPU (sara_b200_compute_matches).  Like the reference, it keeps references to the key lists
+  //! and the returned matches point into their feature vectors.
+  class AnnMatcher
+  {
+  public:
+    AnnMatcher(const KeypointList<OERegion, float>& keys1, const KeypointList<OERegion, float>& keys2,
+               float sift_ratio_thres = 1.2f)
+      : _keys1{keys1}, _keys2{keys2}, _ratio{sift_ratio_thres}
+    {
+      check_sizes();
+    }
+    AnnMatcher(const KeypointList<OERegion, float>& keys, float sift_ratio_thres = 1.2f,
+               float min_max_metric_dist_thres = 0.5f, float pixel_dist_thres = 10.f)
+      : _keys1{keys}, _keys2{keys}, _ratio{sift_ratio_thres}, _metric{min_max_metric_dist_thres}
+      , _pixel{pixel_dist_thres}, _self{true}
+    {
+      check_sizes();
+    }
+
+    std::vector<Match> compute_matches()
+    {
+      const std::vector<OERegion>& f1 = std::get<0>(_keys1);
+      const std::vector<OERegion>& f2 = std::get<0>(_keys2);
+      const DescriptorMatrix& d1 = std::get<1>(_keys1);
+      const DescriptorMatrix& d2 = std::get<1>(_keys2);
+      if (d1.rows() == 0 || d2.rows() == 0)
+        throw std::runtime_error{"Error: the list of key-points is empty!"};  // AnnMatcher.cpp:45-46
+      std::vector<sara_b200_keypoint> k1(f1.size()), k2(f2.size());
+      std::transform(f1.begin(), f1.end(), k1.begin(), to_c_keypoint);
+      std::transform(f2.begin(), f2.end(), k2.begin(), to_c_keypoint);
+      sara_b200_match_args args;
+      sara_b200_default_match_args(&args);
+      args.sift_ratio_thres = _ratio;
+      args.self_matching = _self ? 1 : 0;
+      args.min_max_metric_dist_thres = _metric;
+      args.pixel_dist_thres = _pixel;
+      Context& ctx = default_context(64, 64);
+      std::vector<sara_b200_match> raw(std::max<std::size_t>(1024, 4 * (f1.size() + f2.size())));
+      int n = 0;
+      int rc = sara_b200_compute_matches(ctx.get(), d1.data(), k1.data(), d1.rows(), d2.data(), k2.data(), d2.rows(),
+                                         d1.cols(), 0, &args, raw.data(), static_cast<int>(raw.size()), &n, nullptr);
+      if (rc == SARA_B200_ERR_OVERFLOW && n > static_cast<int>(raw.size()))
+      {
+        raw.resize(n);
+        rc = sara_b200_compute_matches(ctx.get(), d1.data(), k1.data(), d1.rows(), d2.data(), k2.data(), d2.rows(),
+                                       d1.cols(), 0, &args, raw.data(), n, &n, nullptr);
+      }
+      if (rc != 0)
+        rethrow(rc, ctx.get());
+      std::vector<Match> matches;
+      matches.reserve(n);
+      for (int i = 0; i < n; ++i)
+      {
+        const sara_b200_match& m = raw[i];
+        Match out{&f1[m.x_index], &f2[m.y_index], m.score, static_cast<Match::Direction>(m.direction), m.x_index,
+                  m.y_index};
+        out.rank() = m.rank;
+        matches.push_back(out);
+      }
+      return matches;
+    }
+    std::vector<Match> compute_self_matches() { return compute_matches(); }
+
+  private:
+    void check_sizes() const
+    {
+      // size_consistency_predicate (AnnMatcher.cpp:181-184, 198-200)
+      if (static_cast<int>(std::get<0>(_keys1).size()) != std::get<1>(_keys1).rows() ||
+          static_cast<int>(std::get<0>(_keys2).size()) != std::get<1>(_keys2).rows())
+        throw std::runtime_error{"The list of keypoints are inconsistent in size!"};
+    }
+    const KeypointList<OERegion, float>& _keys1;
+    const KeypointList<OERegion, float>& _keys2;
+    float _ratio;
+    float _metric = 0.5f, _pixel = 10.f;
+    bool _self = false;
+  };
+
+  //! DO::Sara::match (SfM/Helpers/KeypointMatching.cpp:19-25)
+  inline std::vector<Match> match(const KeypointList<OERegion, float>& keys1,
+                                  const KeypointList<OERegion, float>& keys2, float lowe_ratio = 0.6f)
+  {
+    AnnMatcher matcher{keys1, keys2, lowe_ratio};
+    return matcher.compute_matches();
+  }
+
 }  // namespace sara_b200
 
 

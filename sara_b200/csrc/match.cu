@@ -13,12 +13,14 @@
 //     a.b ~ hi.hi + lo.hi + hi.lo is accumulated in fp32 by tcgen05.mma (kind::f16, M 128 x N 128
 //     x K 16, operands staged by TMA into 128-byte-swizzled shared memory, accumulators in TMEM,
 //     double buffered).  Four epilogue warps read the accumulators back with tcgen05.ld -- a
-//     thread owns one query row -- and keep that row's 8 best keys |b|^2 - 2 a.b in registers.
-//     Nothing of the N1 x N2 matrix ever reaches memory.
-//  2. EXACT re-ranking.  A warp per query recomputes the FLANN distance of its <= 32 candidates
-//     in fp32 (separate multiply and add, the library is compiled with -fmad=false), orders them
-//     by (distance, index) -- FLANN's result set keeps the first of two equal distances -- and
-//     certifies the result: if the worst key a split kept, minus a bound on the bf16 / fp32
+//     thread owns one query row -- and reduce every chunk of 32 columns to its two smallest keys
+//     |b|^2 - 2 a.b (min / max only, the column index rides in the low mantissa bits): 1/16 of the
+//     N1 x N2 matrix reaches memory, as one float2 per (chunk, query).  A warp per query then picks
+//     the 8 smallest of its row and the floor of everything that was dropped.
+//  2. EXACT re-ranking.  A warp per query recomputes the FLANN distance of its 8 candidates in
+//     fp32 (separate multiply and add, the library is compiled with -fmad=false), orders them by
+//     (distance, index) -- FLANN's result set keeps the first of two equal distances -- and
+//     certifies the result: if the floor of the dropped keys, minus a bound on the bf16 / fp32
 //     error, is not above the k-th exact distance, a dropped point could belong to the answer,
 //     and the query is re-done by the exact scalar kernel below.
 //
@@ -209,7 +211,7 @@ namespace sb {
 
     // ------------------------------------------------------------------------------------------
     // fp32 -> (hi, lo) bf16 split, row layout [hi(128) | lo(128)], rows padded to a multiple of
-    // 128 with zeros; norm[r] = sum x^2 (padded rows: +inf, so that they are never candidates).
+    // 128 with zeros; norm[r] = sum x^2 (padded rows: 1e30, never among the best).
     __global__ void __launch_bounds__(256)
         split_bf16_kernel(const float* __restrict__ src, int n, int n_pad, __nv_bfloat16* __restrict__ dst,
                           float* __restrict__ norm)
@@ -237,7 +239,7 @@ namespace sb {
       for (int d = 16; d > 0; d >>= 1)
         s += __shfl_xor_sync(0xffffffffu, s, d);
       if (lane == 0)
-        norm[warp] = warp < n ? s : __int_as_float(0x7f800000);
+        norm[warp] = warp < n ? s : 1e30f;
     }
 
     // ------------------------------------------------------------------------------------------
@@ -247,6 +249,7 @@ namespace sb {
     constexpr int B_STAGES = 2;
     constexpr int MMA_SMEM = (1 + B_STAGES) * TILE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
     constexpr int TMEM_COLS = 256;                // two accumulator stages of 128 columns
+    constexpr float kBig = 1e30f;                 // |b|^2 of a padding row, and "no key": finite, so that tagging cannot make a NaN
 
     __device__ __forceinline__ void mbar_arrive_plain(void* bar)
     {
@@ -285,9 +288,21 @@ namespace sb {
           "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
           : "memory");
     }
-    __device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32])
+    // (m1 <= m2 <= m3) <- the three smallest of {m1, m2, m3, x}; min / max only
+    __device__ __forceinline__ void insert3(float& m1, float& m2, float& m3, float x)
     {
-      unsigned r[32];
+      const float t1 = fmaxf(m1, x);
+      m1 = fminf(m1, x);
+      const float t2 = fmaxf(m2, t1);
+      m2 = fminf(m2, t1);
+      m3 = fminf(m3, t2);
+    }
+    __device__ __forceinline__ void tmem_ld_wait()
+    {
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    }
+    __device__ __forceinline__ void tmem_ld32_issue(unsigned taddr, unsigned (&r)[32])
+    {
       asm volatile(
           "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
           "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -297,18 +312,14 @@ namespace sb {
             "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
             "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
           : "r"(taddr));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        v[i] = __uint_as_float(r[i]);
     }
 
-    // grid = (query tiles, splits), 256 threads: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM
-    // allocator, warps 4-7 epilogue (warp w reads TMEM lanes 32 (w % 4) ..).
-    __global__ void __launch_bounds__(256, 1)
+    // grid = (query tiles, splits), 384 threads: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM
+    // allocator, warps 4-11 epilogue (warp w reads TMEM lanes 32 (w % 4) ..).
+    __global__ void __launch_bounds__(384, 1)
         knn_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_d,
-                       const float* __restrict__ norm_d, int n_tiles_d, int splits, float* __restrict__ cand_key,
-                       int* __restrict__ cand_idx)
+                       const float* __restrict__ norm_d, int n_tiles_d, int splits, int nq_pad, float2* __restrict__ pairs,
+                       float* __restrict__ floor_split)
     {
       extern __shared__ unsigned char smem_raw[];
       unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -338,7 +349,7 @@ namespace sb {
         for (int s = 0; s < 2; ++s)
         {
           mbar_init(acc_full + s, 1);
-          mbar_init(acc_empty + s, 4);
+          mbar_init(acc_empty + s, 8);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -409,17 +420,20 @@ namespace sb {
       }
       else if (warp >= 4)
       {
-        // ---- epilogue: thread = one query row ----
-        const int row = threadIdx.x - 128;  // TMEM lane
-        const int ew = warp - 4;
-        float kd[KC];
-        int ki[KC];
-#pragma unroll
-        for (int i = 0; i < KC; ++i)
-        {
-          kd[i] = __int_as_float(0x7f800000);
-          ki[i] = -1;
-        }
+        // ---- epilogue: thread = one query row, no data-dependent branch ----
+        // A chunk of 32 accumulator columns becomes 32 keys |b|^2 - 2 a.b whose five low mantissa
+        // bits are replaced by the column's position in the chunk (a perturbation of <= 31 ulp of
+        // an approximate number); the three smallest keys of the chunk are tracked with min / max
+        // only.  The two smallest are stored as one float2, pairs[chunk][query], for select_kernel;
+        // the third is a lower bound of everything the chunk dropped and only its running minimum
+        // is kept (floor_split[split][query]).
+        // Eight epilogue warps: warps 4-7 take the chunks 0, 1 of a tile, warps 8-11 the chunks 2, 3
+        // (a warp reads the TMEM lanes 32 (warp % 4) ..: both groups cover the 128 rows).
+        const int ew = warp & 3;
+        const int half = (warp - 4) >> 2;
+        const int row = 32 * ew + lane;  // TMEM lane
+        const size_t qrow = static_cast<size_t>(blockIdx.x) * 128 + row;
+        float floor3 = kBig;  // the smallest THIRD key of any chunk: everything a chunk dropped is >= it
         for (int i = 0; i < n_my; ++i)
         {
           const int as = i & 1;
@@ -428,40 +442,46 @@ namespace sb {
           tc_fence_after();
           const int jbase = (t0 + i) * 128;
 #pragma unroll 1
-          for (int c = 0; c < 4; ++c)
+          for (int c = 2 * half; c < 2 * half + 2; ++c)
           {
-            float v[32];
+            unsigned r[32];
             __syncwarp();
-            tmem_ld32(tmem_base + (static_cast<unsigned>(32 * ew) << 16) + as * 128 + 32 * c, v);
+            tmem_ld32_issue(tmem_base + (static_cast<unsigned>(32 * ew) << 16) + as * 128 + 32 * c, r);
+            float4 nb[8];  // |b|^2 of the 32 columns: the same addresses for every lane, in flight under the TMEM load
             const float4* nb4 = reinterpret_cast<const float4*>(norm_d + jbase + 32 * c);
 #pragma unroll
             for (int g = 0; g < 8; ++g)
+              nb[g] = __ldg(nb4 + g);
+            tmem_ld_wait();
+            // two independent (smallest, second, third) chains over the even / odd columns
+            float a1 = kBig, a2 = kBig, a3 = kBig, b1 = kBig, b2 = kBig, b3 = kBig;
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
             {
-              const float4 nb = __ldg(nb4 + g);
-              const float k0 = nb.x - 2.f * v[4 * g], k1 = nb.y - 2.f * v[4 * g + 1];
-              const float k2 = nb.z - 2.f * v[4 * g + 2], k3 = nb.w - 2.f * v[4 * g + 3];
-              if (k0 < kd[KC - 1])
-                insert_sorted<KC>(kd, ki, k0, jbase + 32 * c + 4 * g);
-              if (k1 < kd[KC - 1])
-                insert_sorted<KC>(kd, ki, k1, jbase + 32 * c + 4 * g + 1);
-              if (k2 < kd[KC - 1])
-                insert_sorted<KC>(kd, ki, k2, jbase + 32 * c + 4 * g + 2);
-              if (k3 < kd[KC - 1])
-                insert_sorted<KC>(kd, ki, k3, jbase + 32 * c + 4 * g + 3);
+              const float n4[4] = {nb[g].x, nb[g].y, nb[g].z, nb[g].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+              {
+                const float key = __fmaf_rn(-2.f, __uint_as_float(r[4 * g + e]), n4[e]);
+                const float x = __int_as_float((__float_as_int(key) & ~31) | (4 * g + e));
+                if (e & 1)
+                  insert3(b1, b2, b3, x);
+                else
+                  insert3(a1, a2, a3, x);
+              }
             }
+            insert3(a1, a2, a3, b1);
+            insert3(a1, a2, a3, b2);
+            insert3(a1, a2, a3, b3);
+            pairs[(static_cast<size_t>(jbase / 32 + c)) * nq_pad + qrow] = make_float2(a1, a2);
+            floor3 = fminf(floor3, a3);
           }
           tc_fence_before();
           __syncwarp();
           if (lane == 0)
             mbar_arrive_plain(acc_empty + as);
         }
-        const size_t base = ((static_cast<size_t>(blockIdx.x) * 128 + row) * splits + blockIdx.y) * KC;
-#pragma unroll
-        for (int i = 0; i < KC; ++i)
-        {
-          cand_key[base + i] = kd[i];
-          cand_idx[base + i] = ki[i];
-        }
+        floor_split[(static_cast<size_t>(blockIdx.y) * 2 + half) * nq_pad + qrow] = floor3;
       }
 
       tc_fence_before();
@@ -474,17 +494,204 @@ namespace sb {
     }
 
     // ------------------------------------------------------------------------------------------
+    // Exact search for a FEW queries (the uncertified ones): a block per query, a thread per data
+    // row (strided), the query broadcast from shared memory; thread-private sorted lists, merged
+    // by KC rounds of a block-wide minimum over (distance, index).
+    // grid.y slices of the data range share a query; every block writes its KC best as exact
+    // candidates, cand[(q * slices + slice) * KC + i], for rerank_kernel to merge.
+    __global__ void __launch_bounds__(512)
+        knn_few_kernel(const float* __restrict__ queries, const int* __restrict__ qlist, const float* __restrict__ data,
+                       int nd, int dim, float* __restrict__ cand_key, int* __restrict__ cand_idx)
+    {
+      extern __shared__ float smem[];
+      float* qv = smem;  // dim floats
+      __shared__ float r_d[16];
+      __shared__ int r_i[16];
+      const int q = qlist[blockIdx.x];
+      for (int d = threadIdx.x; d < dim; d += blockDim.x)
+        qv[d] = queries[static_cast<size_t>(q) * dim + d];
+      __syncthreads();
+      float kd[KC];
+      int ki[KC];
+#pragma unroll
+      for (int i = 0; i < KC; ++i)
+      {
+        kd[i] = FLT_MAX;
+        ki[i] = -1;
+      }
+      const bool vec = (dim & 3) == 0 && (reinterpret_cast<uintptr_t>(data) & 15) == 0;
+      const int slices = gridDim.y;
+      const int per = (nd + slices - 1) / slices;
+      const int j_end = min(nd, (static_cast<int>(blockIdx.y) + 1) * per);
+      for (int j = blockIdx.y * per + threadIdx.x; j < j_end; j += blockDim.x)
+      {
+        const float* b = data + static_cast<size_t>(j) * dim;
+        float result = 0.f;
+        int i = 0;
+        if (vec)
+          for (; i + 3 < dim; i += 4)
+          {
+            const float4 x = __ldg(reinterpret_cast<const float4*>(b + i));
+            const float d0 = x.x - qv[i], d1 = x.y - qv[i + 1], d2 = x.z - qv[i + 2], d3 = x.w - qv[i + 3];
+            result += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+          }
+        else
+          for (; i + 3 < dim; i += 4)
+          {
+            const float d0 = b[i] - qv[i], d1 = b[i + 1] - qv[i + 1], d2 = b[i + 2] - qv[i + 2], d3 = b[i + 3] - qv[i + 3];
+            result += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+          }
+        for (; i < dim; ++i)
+        {
+          const float d0 = b[i] - qv[i];
+          result += d0 * d0;
+        }
+        if (result < kd[KC - 1])
+          insert_sorted<KC>(kd, ki, result, j);  // j ascends within a thread: equal distances keep the lower index first
+      }
+      // k rounds: the block-wide smallest (distance, index) among the list heads; its owner pops it
+      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+      for (int round = 0; round < KC; ++round)
+      {
+        float bd = kd[0];
+        int bi = ki[0] >= 0 ? ki[0] : INT_MAX;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+        {
+          const float od = __shfl_xor_sync(0xffffffffu, bd, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (od < bd || (od == bd && oi < bi))
+          {
+            bd = od;
+            bi = oi;
+          }
+        }
+        if (lane == 0)
+        {
+          r_d[warp] = bd;
+          r_i[warp] = bi;
+        }
+        __syncthreads();
+        float gd = r_d[0];
+        int gi = r_i[0];
+        for (int w2 = 1; w2 < static_cast<int>(blockDim.x >> 5); ++w2)
+          if (r_d[w2] < gd || (r_d[w2] == gd && r_i[w2] < gi))
+          {
+            gd = r_d[w2];
+            gi = r_i[w2];
+          }
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+          const size_t at = (static_cast<size_t>(q) * slices + blockIdx.y) * KC + round;
+          cand_idx[at] = gi == INT_MAX ? -1 : gi;
+          cand_key[at] = gi == INT_MAX ? FLT_MAX : gd;
+        }
+        if (ki[0] == gi && gi != INT_MAX)  // pop
+        {
+#pragma unroll
+          for (int i = 0; i + 1 < KC; ++i)
+          {
+            kd[i] = kd[i + 1];
+            ki[i] = ki[i + 1];
+          }
+          kd[KC - 1] = FLT_MAX;
+          ki[KC - 1] = -1;
+        }
+      }
+    }
+
+    // ------------------------------------------------------------------------------------------
+    // Selection: the KC smallest tagged keys of every query row.  Block = 32 queries x 8 parts: a
+    // lane is a query (the float2 reads of a warp are 256 contiguous bytes), warp p scans the chunks
+    // c = p (mod 8) into a thread-private sorted list; the lists meet in shared memory and warp 0
+    // merges the eight lists of its queries.  Output: cand_key / cand_idx[q * KC + i] (data index
+    // decoded from the chunk number and the five tag bits) and floor_key[q] = the smallest key that
+    // was dropped anywhere: min(third keys of the chunks, the KC-th key taken here).
+    constexpr int SEL_PARTS = 8;
+    __global__ void __launch_bounds__(32 * SEL_PARTS)
+        select_kernel(const float2* __restrict__ pairs, const float* __restrict__ floor_split, int splits, int nq,
+                      int nq_pad, int nd, int n_chunks, float* __restrict__ cand_key, int* __restrict__ cand_idx,
+                      float* __restrict__ floor_key)
+    {
+      __shared__ float s_kd[SEL_PARTS][KC][32];
+      __shared__ int s_ki[SEL_PARTS][KC][32];
+      const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
+      const int q = blockIdx.x * 32 + lane;  // < nq_pad: the padded rows hold finite garbage
+      float kd[KC];
+      int ki[KC];
+#pragma unroll
+      for (int i = 0; i < KC; ++i)
+      {
+        kd[i] = kBig;
+        ki[i] = -1;
+      }
+      for (int c0 = part; c0 < n_chunks; c0 += 4 * SEL_PARTS)
+      {
+        float2 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+        {
+          const int c = c0 + u * SEL_PARTS;
+          v[u] = c < n_chunks ? __ldg(pairs + static_cast<size_t>(c) * nq_pad + q) : make_float2(kBig, kBig);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+        {
+          const int c = c0 + u * SEL_PARTS;
+          if (v[u].x < kd[KC - 1])
+          {
+            insert_sorted<KC>(kd, ki, v[u].x, c * 32 + (__float_as_int(v[u].x) & 31));
+            if (v[u].y < kd[KC - 1])
+              insert_sorted<KC>(kd, ki, v[u].y, c * 32 + (__float_as_int(v[u].y) & 31));
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < KC; ++i)
+      {
+        s_kd[part][i][lane] = kd[i];
+        s_ki[part][i][lane] = ki[i];
+      }
+      __syncthreads();
+      if (part != 0)
+        return;
+      for (int p = 1; p < SEL_PARTS; ++p)
+#pragma unroll 1
+        for (int i = 0; i < KC; ++i)
+        {
+          const float x = s_kd[p][i][lane];
+          if (!(x < kd[KC - 1]))
+            break;  // the lists are sorted
+          insert_sorted<KC>(kd, ki, x, s_ki[p][i][lane]);
+        }
+      if (q >= nq)
+        return;
+      float fl = kd[KC - 1];
+      for (int sp = 0; sp < splits; ++sp)
+        fl = fminf(fl, floor_split[static_cast<size_t>(sp) * nq_pad + q]);
+      floor_key[q] = fl;
+#pragma unroll
+      for (int i = 0; i < KC; ++i)
+      {
+        const bool real = kd[i] < kBig * 0.5f && ki[i] >= 0 && ki[i] < nd;
+        cand_key[static_cast<size_t>(q) * KC + i] = real ? kd[i] : kBig;
+        cand_idx[static_cast<size_t>(q) * KC + i] = real ? ki[i] : -1;
+      }
+    }
+
+    // ------------------------------------------------------------------------------------------
     // Re-ranking: a warp per query, one candidate per lane (splits * KC <= 32).
-    //   approx != 0: keys are |b|^2 - 2 a.b from the tensor cores: recompute the exact distance of
-    //                every candidate and certify; uncertified queries are appended to `redo`.
+    //   approx != 0: the KC candidates of select_kernel (splits = 1): recompute the exact distance of
+    //                every candidate and certify against floor_key; uncertified queries are appended to `redo`.
     //   approx == 0: keys are exact distances already.
     // Output: k entries per query, ascending (distance, index); unused entries (-1, FLT_MAX).
     __global__ void __launch_bounds__(256)
         rerank_kernel(const float* __restrict__ queries, const int* __restrict__ qlist, int nq,
                       const float* __restrict__ data, int nd, int dim, int splits, int k, int approx,
-                      const float* __restrict__ norm_q, const float* __restrict__ cand_key,
-                      const int* __restrict__ cand_idx, int* __restrict__ out_idx, float* __restrict__ out_dist,
-                      int* __restrict__ redo, int* __restrict__ n_redo)
+                      const float* __restrict__ norm_q, const float* __restrict__ floor_key,
+                      const float* __restrict__ cand_key, const int* __restrict__ cand_idx, int* __restrict__ out_idx,
+                      float* __restrict__ out_dist, int* __restrict__ redo, int* __restrict__ n_redo)
     {
       const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
       if (w >= nq)
@@ -528,17 +735,13 @@ namespace sb {
         const int kth = min(k, n_valid) - 1;
         const unsigned who = __ballot_sync(0xffffffffu, idx >= 0 && rank == kth);
         const float dk = who ? __shfl_sync(0xffffffffu, d, __ffs(who) - 1) : FLT_MAX;
-        // the smallest key any split may have dropped: its KC-th kept key (inf when the split kept everything)
-        float thr = __int_as_float(0x7f800000);
-        if (lane < C && (lane % KC) == KC - 1 && idx >= 0)
-          thr = key;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-          thr = fminf(thr, __shfl_xor_sync(0xffffffffu, thr, o));
+        // everything the candidate pass dropped has a key >= floor_key[q] (select_kernel); a floor of
+        // kBig means nothing real was dropped
+        const float thr = floor_key[q];
         const float na = norm_q[q];
         const float thr_dist = na + thr;
-        const float eps = 1e-3f * (fabsf(na) + fabsf(thr_dist)) + 1.f;
-        const bool kept_all = !(thr < __int_as_float(0x7f800000));  // no split dropped anything
+        const float eps = 2.5e-4f * (fabsf(na) + fabsf(thr_dist)) + 1.f;  // >> the bf16-split / fp32 error, ~3e-5 (|a|^2 + |b|^2)
+        const bool kept_all = !(thr < kBig * 0.5f);
         const bool certain = n_valid >= min(k, nd) && (kept_all || thr_dist - eps > dk);
         if (!certain && lane == 0)
           redo[atomicAdd(n_redo, 1)] = q;
@@ -635,9 +838,22 @@ namespace sb {
       const int nq_pad = (nq + 127) / 128 * 128, nd_pad = (nd + 127) / 128 * 128;
       const int q_tiles = nq_pad / 128, d_tiles = nd_pad / 128;
       int splits = 1;
+      int mma_splits = 1;
       if (use_mma)
-        while (splits < MAX_SPLITS && q_tiles * splits * 2 <= 148 && d_tiles >= 2 * splits * 2)
-          splits *= 2;
+      {
+        // one CTA per SM; CTAs of a query tile write disjoint chunks, so any split count works:
+        // pick the one that minimises (waves) x (tiles per CTA)
+        long best = LONG_MAX;
+        for (int sp = 1; sp <= 16 && sp <= d_tiles; ++sp)
+        {
+          const long cost = static_cast<long>((q_tiles * sp + 147) / 148) * ((d_tiles + sp - 1) / sp);
+          if (cost < best)
+          {
+            best = cost;
+            mma_splits = sp;
+          }
+        }
+      }
       else
         while (splits < MAX_SPLITS && ((nq + QB - 1) / QB) * splits * 2 <= 2 * 148 && nd >= 2 * splits * 4 * TJ)
           splits *= 2;
@@ -655,6 +871,9 @@ namespace sb {
         add(static_cast<size_t>(nd_pad) * 512);
         add(static_cast<size_t>(nq_pad) * 4);
         add(static_cast<size_t>(nd_pad) * 4);
+        add(static_cast<size_t>(nq_pad) * 4);                      // floor keys
+        add(static_cast<size_t>(nq_pad) * 32 * 4);                 // third-key floors per (split, epilogue half)
+        add(static_cast<size_t>(nd_pad / 32) * nq_pad * 8);        // two best keys per (chunk, query)
       }
       if (need > ws.bytes)
       {
@@ -683,6 +902,9 @@ namespace sb {
         __nv_bfloat16* db = carve<__nv_bfloat16>(cur, static_cast<size_t>(nd_pad) * 256);
         float* norm_q = carve<float>(cur, nq_pad);
         float* norm_d = carve<float>(cur, nd_pad);
+        float* floor_key = carve<float>(cur, nq_pad);
+        float* floor_split = carve<float>(cur, static_cast<size_t>(nq_pad) * 32);
+        float2* pairs = carve<float2>(cur, static_cast<size_t>(nd_pad / 32) * nq_pad);
         CUtensorMap map_q, map_d;
         if (!encode_map(&map_q, qb, nq_pad) || !encode_map(&map_d, db, nd_pad))
         {
@@ -692,11 +914,14 @@ namespace sb {
         cudaMemsetAsync(n_redo, 0, 4, st);
         split_bf16_kernel<<<(nq_pad * 32 + 255) / 256, 256, 0, st>>>(d_q, nq, nq_pad, qb, norm_q);
         split_bf16_kernel<<<(nd_pad * 32 + 255) / 256, 256, 0, st>>>(d_data, nd, nd_pad, db, norm_d);
-        knn_mma_kernel<<<dim3(q_tiles, splits), 256, MMA_SMEM, st>>>(map_q, map_d, norm_d, d_tiles, splits, cand_key,
-                                                                     cand_idx);
-        rerank_kernel<<<(nq * 32 + 255) / 256, 256, 0, st>>>(d_q, nullptr, nq, d_data, nd, dim, splits, k, 1, norm_q,
+        knn_mma_kernel<<<dim3(q_tiles, mma_splits), 384, MMA_SMEM, st>>>(map_q, map_d, norm_d, d_tiles, mma_splits, nq_pad,
+                                                                         pairs, floor_split);
+        select_kernel<<<nq_pad / 32, 32 * SEL_PARTS, 0, st>>>(pairs, floor_split, 2 * mma_splits, nq, nq_pad, nd, nd_pad / 32,
+                                                              cand_key, cand_idx, floor_key);
+        rerank_kernel<<<(nq * 32 + 255) / 256, 256, 0, st>>>(d_q, nullptr, nq, d_data, nd, dim, 1, k, 1, norm_q, floor_key,
                                                              cand_key, cand_idx, d_idx, d_dist, redo, n_redo);
-        launches += 4;
+        launches += 5;
+        splits = mma_splits;
         int h_redo = 0;
         if (cudaMemcpyAsync(&h_redo, n_redo, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
             cudaStreamSynchronize(st) != cudaSuccess)
@@ -707,15 +932,29 @@ namespace sb {
         if (h_redo > 0)
         {
           // uncertified queries: exact scalar search over the whole data set
-          int s2 = 1;
-          while (s2 < MAX_SPLITS && ((h_redo + QB - 1) / QB) * s2 * 2 <= 2 * 148 && nd >= 2 * s2 * 4 * TJ)
-            s2 *= 2;
-          knn_exact_kernel<0><<<dim3((h_redo + QB - 1) / QB, s2), QB, ex_smem, st>>>(
-              d_q, redo, h_redo, d_data, nd, dim, s2, cand_key, cand_idx, nullptr, nullptr, nullptr, nullptr, nullptr,
-              nullptr);
-          rerank_kernel<<<(h_redo * 32 + 255) / 256, 256, 0, st>>>(d_q, redo, h_redo, d_data, nd, dim, s2, k, 0, nullptr,
-                                                                 cand_key, cand_idx, d_idx, d_dist, nullptr, nullptr);
-          launches += 2;
+          if (h_redo <= 4096)
+          {
+            const int slices = nd >= 4096 ? MAX_SPLITS : 1;
+            knn_few_kernel<<<dim3(h_redo, slices), 512, dim * sizeof(float), st>>>(d_q, redo, d_data, nd, dim, cand_key,
+                                                                                  cand_idx);
+            rerank_kernel<<<(h_redo * 32 + 255) / 256, 256, 0, st>>>(d_q, redo, h_redo, d_data, nd, dim, slices, k, 0, nullptr,
+                                                                   nullptr, cand_key, cand_idx, d_idx, d_dist, nullptr,
+                                                                   nullptr);
+            launches += 2;
+          }
+          else
+          {
+            int s2 = 1;
+            while (s2 < MAX_SPLITS && ((h_redo + QB - 1) / QB) * s2 * 2 <= 2 * 148 && nd >= 2 * s2 * 4 * TJ)
+              s2 *= 2;
+            knn_exact_kernel<0><<<dim3((h_redo + QB - 1) / QB, s2), QB, ex_smem, st>>>(
+                d_q, redo, h_redo, d_data, nd, dim, s2, cand_key, cand_idx, nullptr, nullptr, nullptr, nullptr, nullptr,
+                nullptr);
+            rerank_kernel<<<(h_redo * 32 + 255) / 256, 256, 0, st>>>(d_q, redo, h_redo, d_data, nd, dim, s2, k, 0, nullptr,
+                                                                   nullptr, cand_key, cand_idx, d_idx, d_dist, nullptr,
+                                                                   nullptr);
+            launches += 2;
+          }
         }
         if (stats)
         {
@@ -728,7 +967,7 @@ namespace sb {
         knn_exact_kernel<0><<<dim3((nq + QB - 1) / QB, splits), QB, ex_smem, st>>>(
             d_q, nullptr, nq, d_data, nd, dim, splits, cand_key, cand_idx, nullptr, nullptr, nullptr, nullptr, nullptr,
             nullptr);
-        rerank_kernel<<<(nq * 32 + 255) / 256, 256, 0, st>>>(d_q, nullptr, nq, d_data, nd, dim, splits, k, 0, nullptr,
+        rerank_kernel<<<(nq * 32 + 255) / 256, 256, 0, st>>>(d_q, nullptr, nq, d_data, nd, dim, splits, k, 0, nullptr, nullptr,
                                                              cand_key, cand_idx, d_idx, d_dist, nullptr, nullptr);
         launches += 2;
       }

@@ -82,3 +82,102 @@ def test_cpp_compute_sift_keypoints_matches_python(tmp_path):
     assert np.array_equal(rec[:, 2], f["shape"][:, 0]) and np.array_equal(rec[:, 3], f["orientation"])
     assert np.array_equal(rec[:, 4], f["extremum_value"]) and np.array_equal(rec[:, 5], f["extremum_type"].astype(np.float32))
     assert desc.tobytes() == sb.descriptors(kl).tobytes()
+
+
+MATCH_PROGRAM = r"""
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "sara_b200.hpp"
+
+namespace sara = sara_b200;
+using Keys = sara::KeypointList<sara::OERegion, float>;
+
+static Keys make_keys(int n, int dim)
+{
+  return Keys{std::vector<sara::OERegion>(n), sara::DescriptorMatrix{n, dim}};
+}
+
+int main(int argc, char** argv)
+{
+  // cpp/test/Sara/FeatureMatching/test_featurematching_matching.cpp:27-57
+  {
+    auto keys1 = make_keys(1, 2);
+    auto keys2 = make_keys(10, 2);
+    for (int i = 0; i < 10; ++i)
+    {
+      std::get<0>(keys2)[i].coords(0) = std::get<0>(keys2)[i].coords(1) = float(i);
+      std::get<1>(keys2).data()[2 * i] = std::get<1>(keys2).data()[2 * i + 1] = float(i);
+    }
+    constexpr auto nearest_neighbor_ratio = 0.6f;
+    sara::AnnMatcher matcher{keys1, keys2, nearest_neighbor_ratio};
+    auto matches = matcher.compute_matches();
+    if (matches.size() != 1u)
+      return 10;
+    const auto& m = matches.front();
+    if (&m.x() != &std::get<0>(keys1)[0] || &m.y() != &std::get<0>(keys2)[0] || m.score() != 0.f)
+      return 11;
+  }
+  // empty key list: "the list of key-points is empty" (AnnMatcher.cpp:45-46) -> std::runtime_error
+  try
+  {
+    auto a = make_keys(3, 128), b = make_keys(0, 128);
+    sara::AnnMatcher{a, b, 0.6f}.compute_matches();
+    return 12;
+  }
+  catch (const std::runtime_error&)
+  {
+  }
+  // two descriptor sets from files: n1, n2, then the rows
+  FILE* f = std::fopen(argv[1], "rb");
+  int n[2];
+  if (!f || std::fread(n, sizeof(int), 2, f) != 2)
+    return 2;
+  auto k1 = make_keys(n[0], 128), k2 = make_keys(n[1], 128);
+  if (std::fread(std::get<1>(k1).data(), sizeof(float), size_t(n[0]) * 128, f) != size_t(n[0]) * 128 ||
+      std::fread(std::get<1>(k2).data(), sizeof(float), size_t(n[1]) * 128, f) != size_t(n[1]) * 128)
+    return 3;
+  std::fclose(f);
+  for (int i = 0; i < n[0]; ++i)
+    std::get<0>(k1)[i].coords(0) = float(i);  // distinct features (Match::operator== compares features)
+  for (int i = 0; i < n[1]; ++i)
+    std::get<0>(k2)[i].coords(0) = float(i);
+  const auto matches = sara::match(k1, k2, 0.8f);  // SfM/Helpers/KeypointMatching.cpp:19-25
+  f = std::fopen(argv[2], "wb");
+  for (const auto& m : matches)
+  {
+    const int rec[3] = {m.x_index(), m.y_index(), m.rank()};
+    const float s = m.score();
+    std::fwrite(rec, sizeof(int), 3, f);
+    std::fwrite(&s, sizeof(float), 1, f);
+  }
+  std::fclose(f);
+  return 0;
+}
+"""
+
+
+def test_cpp_ann_matcher(tmp_path):
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "match_flann.npz"))
+    d1, d2 = gold["d1"], gold["d2"]
+    inp = tmp_path / "desc.bin"
+    with open(inp, "wb") as f:
+        np.array([len(d1), len(d2)], np.int32).tofile(f)
+        d1.tofile(f)
+        d2.tofile(f)
+    src = tmp_path / "match.cpp"
+    src.write_text(MATCH_PROGRAM)
+    exe = tmp_path / "match"
+    lib = sb.library_path()
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), lib,
+                           f"-Wl,-rpath,{os.path.dirname(lib)}"])
+    out = tmp_path / "matches.bin"
+    assert subprocess.call([str(exe), str(inp), str(out)]) == 0
+    rec = np.fromfile(out, dtype=np.dtype([("x", "<i4"), ("y", "<i4"), ("rank", "<i4"), ("score", "<f4")]))
+    from oracle import match as M
+
+    ref = M.ann_match(d1, d2, 0.8)
+    assert len(rec) == len(ref) > 100
+    assert np.array_equal(rec["x"], ref["x_index"]) and np.array_equal(rec["y"], ref["y_index"])
+    assert np.array_equal(rec["rank"], ref["rank"])
+    assert np.array_equal(rec["score"].view(np.uint32), ref["score"].view(np.uint32))
