@@ -227,6 +227,22 @@ SARA_B200_API int sara_b200_wait(sara_b200_ctx* ctx, int slot, int* n_out);
 SARA_B200_API int sara_b200_dog_extrema(sara_b200_ctx* ctx, int slot, const float* image, int w, int h,
                           int image_on_device, const sara_b200_dog_args* args);
 
+/* ---- sibling detectors on the same pyramid ------------------------------------
+ * ComputeLoGExtrema::operator() (FeatureDetectors/LoG.hpp:71-99, LoG.cpp:20-58) and
+ * ComputeDoHExtrema::operator() (FeatureDetectors/Hessian.hpp:195-224, Hessian.cpp:59-98):
+ * gaussian_pyramid, then laplacian_pyramid (GaussianPyramid.hpp:156-178) resp.
+ * det_of_hessian_pyramid (Hessian.hpp:35-57) -- as many layers as the Gaussian pyramid --
+ * and local_scale_space_extrema on s = 1 .. N - 2.  `gauss_truncate` of the args is not used
+ * (both functors call gaussian_pyramid with its default).  Results stay in the slot: the
+ * function pyramid is read with sara_b200_copy_layer(which = 1, s < N), the extrema with
+ * sara_b200_copy_extrema.  Reference defaults: LoG ImagePyramidParams(-1, 3 + 2), thres 0.01,
+ * edge ratio 10, padding 1, 5 iterations; DoH ImagePyramidParams(-1, 3 + 2, 2^(1/3), 2),
+ * thres 1e-6, edge ratio 10, padding 1, 2 iterations. */
+SARA_B200_API int sara_b200_log_extrema(sara_b200_ctx* ctx, int slot, const float* image, int w, int h,
+                          int image_on_device, const sara_b200_dog_args* args);
+SARA_B200_API int sara_b200_doh_extrema(sara_b200_ctx* ctx, int slot, const float* image, int w, int h,
+                          int image_on_device, const sara_b200_dog_args* args);
+
 /* ---- gaussian_pyramid + difference_of_gaussians_pyramid only --------------
  * (GaussianPyramid.hpp:35-125, GaussianPyramid.cpp:23-51): the "fused pyramid
  * + DoG" benchmark configuration.  Asynchronous on the slot's stream (or

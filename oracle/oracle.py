@@ -71,6 +71,11 @@ def lib() -> C.CDLL:
             C.c_float, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int,
             C.POINTER(C.c_void_p),
         ]
+        L.oracle_function_extrema.argtypes = [
+            fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float,
+            C.c_float, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int,
+            C.POINTER(C.c_void_p),
+        ]
         for name in (
             "oracle_free", "oracle_num_octaves", "oracle_num_scales",
             "oracle_num_extrema", "oracle_num_keypoints",
@@ -432,4 +437,26 @@ def compute_dog_extrema(
         _p(img), w, h, pp[0], pp[1], pp[2], pp[3], pp[4], pp[5], pp[6],
         gauss_truncate, extremum_thres, edge_ratio_thres, int(img_padding_sz),
         int(extremum_refinement_iter), C.byref(out)))
+    return SiftResult(out)
+
+
+def compute_function_extrema(
+    image,
+    which: str,
+    pyramid_params: PyramidParams | None = None,
+    extremum_thres: float = 0.01,
+    edge_ratio_thres: float = 10.0,
+    img_padding_sz: int = 1,
+    extremum_refinement_iter: int = 5,
+) -> SiftResult:
+    """ComputeLoGExtrema (FeatureDetectors/LoG.hpp:71-83, LoG.cpp:20-58; which = "log") or
+    ComputeDoHExtrema (FeatureDetectors/Hessian.cpp:59-98; which = "doh").  Defaults of both
+    constructors: ImagePyramidParams(-1, 3 + 2).  The function pyramid is layer kind 1."""
+    img = _f32(image)
+    h, w = img.shape
+    pp = (pyramid_params or PyramidParams(scale_count_per_octave=5)).astuple()
+    out = C.c_void_p()
+    _check(lib().oracle_function_extrema(
+        _p(img), w, h, pp[0], pp[1], pp[2], pp[3], pp[4], pp[5], pp[6], {"log": 1, "doh": 2}[which],
+        extremum_thres, edge_ratio_thres, int(img_padding_sz), int(extremum_refinement_iter), C.byref(out)))
     return SiftResult(out)

@@ -1140,6 +1140,102 @@ namespace oracle {
       }
   }
 
+  // ------------------------------------------------------------------------ //
+  // Sibling detectors on the same pyramid.
+  // ImageProcessing/Differential.hpp:106-135 Laplacian functor (N = 2, borders replicated) and
+  // ImageProcessing/GaussianPyramid.hpp:156-178 laplacian_pyramid: every layer times
+  // float(square(scale_relative_to_octave(s))) (the square is taken in double).
+  Pyramid laplacian_pyramid(const Pyramid& gaussians)
+  {
+    Pyramid L;
+    L.reset(gaussians.num_octaves, gaussians.num_scales, gaussians.scale_initial,
+            gaussians.scale_geometric_factor);
+    for (int o = 0; o < L.num_octaves; ++o)
+    {
+      L.oct_scaling[o] = gaussians.oct_scaling[o];
+      for (int s = 0; s < L.num_scales; ++s)
+      {
+        const Image& g = gaussians(s, o);
+        Image l(g.w, g.h);
+        const double sr = gaussians.scale_relative_to_octave(s);
+        const float norm = static_cast<float>(sr * sr);
+        for (int y = 0; y < g.h; ++y)
+          for (int x = 0; x < g.w; ++x)
+          {
+            const float c = g(x, y);
+            float value = 0.f;
+            if (x == 0)
+              value += g(x + 1, y) + c;
+            else if (x == g.w - 1)
+              value += c + g(x - 1, y);
+            else
+              value += g(x + 1, y) + g(x - 1, y);
+            if (y == 0)
+              value += g(x, y + 1) + c;
+            else if (y == g.h - 1)
+              value += c + g(x, y - 1);
+            else
+              value += g(x, y + 1) + g(x, y - 1);
+            float out = value - 4 * c;  // 2 * N * (*in)
+            out *= norm;
+            l(x, y) = out;
+          }
+        L(s, o) = std::move(l);
+      }
+    }
+    return L;
+  }
+
+  // FeatureDetectors/Hessian.hpp:35-57 det_of_hessian_pyramid: Hessian functor
+  // (Differential.hpp:191-226), 2 x 2 determinant, times float(quartic(scale)) (quartic in double).
+  Pyramid det_of_hessian_pyramid(const Pyramid& gaussians)
+  {
+    Pyramid D;
+    D.reset(gaussians.num_octaves, gaussians.num_scales, gaussians.scale_initial,
+            gaussians.scale_geometric_factor);
+    for (int o = 0; o < D.num_octaves; ++o)
+    {
+      D.oct_scaling[o] = gaussians.oct_scaling[o];
+      for (int s = 0; s < D.num_scales; ++s)
+      {
+        const Image& g = gaussians(s, o);
+        Image d(g.w, g.h);
+        const double sr = gaussians.scale_relative_to_octave(s);
+        const float norm = static_cast<float>(sr * sr * sr * sr);
+        for (int y = 0; y < g.h; ++y)
+          for (int x = 0; x < g.w; ++x)
+          {
+            float H[4];
+            hessian2(g, x, y, H);
+            float det = H[0] * H[3] - H[2] * H[1];  // Eigen 2 x 2 determinant
+            det *= norm;
+            d(x, y) = det;
+          }
+        D(s, o) = std::move(d);
+      }
+    }
+    return D;
+  }
+
+  // FeatureDetectors/LoG.cpp:20-58 ComputeLoGExtrema::operator() (which = 1) and
+  // FeatureDetectors/Hessian.cpp:59-98 ComputeDoHExtrema::operator() (which = 2): the function
+  // pyramid has as many layers as the Gaussian one, extrema are searched on s = 1 .. N - 2.
+  void compute_function_extrema(const Image& image, const PyramidParams& pp, int which,
+                                float extremum_thres, float edge_ratio_thres,
+                                int img_padding_sz, int extremum_refinement_iter, Result& R)
+  {
+    R.G = gaussian_pyramid(image, pp, 4.f);
+    R.D = which == 1 ? laplacian_pyramid(R.G) : det_of_hessian_pyramid(R.G);
+    R.extrema.clear();
+    for (int o = 0; o < R.D.num_octaves; ++o)
+      for (int s = 1; s < R.D.num_scales - 1; ++s)
+      {
+        auto e = local_scale_space_extrema(R.D, s, o, extremum_thres, edge_ratio_thres,
+                                           img_padding_sz, extremum_refinement_iter);
+        R.extrema.insert(R.extrema.end(), e.begin(), e.end());
+      }
+  }
+
   // FeatureDetectors/SIFT.cpp:27-108 compute_sift_keypoints.
   void compute_sift_keypoints(const Image& image, const PyramidParams& pp,
                               float gauss_truncate, float extremum_thres,
@@ -1562,6 +1658,30 @@ int oracle_dog_extrema(const float* image, int w, int h, int fo, int ns, float k
                         make_params(fo, ns, k, pad, cam, init, omax),
                         gauss_truncate, extremum_thres, edge_ratio_thres,
                         img_padding_sz, refine_iter, *R);
+  }
+  catch (...)
+  {
+    delete R;
+    throw;
+  }
+  *out = R;
+  return 0;
+  ORACLE_CATCH
+}
+
+// ComputeLoGExtrema (which = 1) / ComputeDoHExtrema (which = 2); the function pyramid is
+// read back as layer kind 1 (in place of the DoG).
+int oracle_function_extrema(const float* image, int w, int h, int fo, int ns, float k,
+                            int pad, float cam, float init, int omax, int which,
+                            float extremum_thres, float edge_ratio_thres,
+                            int img_padding_sz, int refine_iter, void** out)
+{
+  ORACLE_TRY
+  auto* R = new Result;
+  try
+  {
+    compute_function_extrema(make_image(image, w, h), make_params(fo, ns, k, pad, cam, init, omax),
+                             which, extremum_thres, edge_ratio_thres, img_padding_sz, refine_iter, *R);
   }
   catch (...)
   {

@@ -11,6 +11,8 @@ from .api import (  # noqa: F401
     MATCH_DTYPE,
     match,
     ComputeDoGExtrema,
+    ComputeDoHExtrema,
+    ComputeLoGExtrema,
     ImagePyramidParams,
     KEYPOINT_DTYPE,
     KeypointList,

@@ -113,6 +113,7 @@ SYMBOLS = [
     "sara_b200_make_gaussian_kernel", "sara_b200_sift_u8", "sara_b200_sift_enqueue_u8", "sara_b200_to_gray32f",
     "sara_b200_collect_device", "sara_b200_set_graphs",
     "sara_b200_default_match_args", "sara_b200_knn", "sara_b200_compute_matches",
+    "sara_b200_log_extrema", "sara_b200_doh_extrema",
 ]
 
 
@@ -157,6 +158,8 @@ def load_library() -> C.CDLL:
     L.sara_b200_device_results.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), ip]
     L.sara_b200_wait.argtypes = [vp, C.c_int, ip]
     L.sara_b200_dog_extrema.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.POINTER(_DogArgs)]
+    L.sara_b200_log_extrema.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.POINTER(_DogArgs)]
+    L.sara_b200_doh_extrema.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.POINTER(_DogArgs)]
     L.sara_b200_pyramid_enqueue.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.POINTER(_PyrParams), C.c_float, vp]
     L.sara_b200_num_octaves.argtypes = [vp, C.c_int]
     L.sara_b200_num_scales.argtypes = [vp, C.c_int]
@@ -473,6 +476,18 @@ class SiftContext:
         del keep
         return self.extrema(slot)
 
+    def function_extrema(self, which: str, image, pyramid_params=None, extremum_thres=0.01, edge_ratio_thres=10.0,
+                         img_padding_sz=1, extremum_refinement_iter=5, slot=0) -> np.ndarray:
+        """ComputeLoGExtrema (which = "log") / ComputeDoHExtrema ("doh"): the function pyramid is then read with
+        dog_layer(s, o) for s < num_scales()."""
+        ptr, w, h, on_dev, keep = _as_image(image)
+        args = _DogArgs((pyramid_params or ImagePyramidParams(scale_count_per_octave=5))._c(), 4.0, extremum_thres,
+                        edge_ratio_thres, int(img_padding_sz), int(extremum_refinement_iter))
+        fn = {"log": self._L.sara_b200_log_extrema, "doh": self._L.sara_b200_doh_extrema}[which]
+        self._check(fn(self._ctx, slot, ptr, w, h, int(on_dev), C.byref(args)))
+        del keep
+        return self.extrema(slot)
+
     # ---- stage accessors -----------------------------------------------------------------
     def num_octaves(self, slot=0) -> int:
         return self._L.sara_b200_num_octaves(self._ctx, slot)
@@ -572,6 +587,54 @@ class ComputeDoGExtrema:
     def extrema(self, s, o):
         e = self._ctx.extrema()
         return e[(e["s"] == s) & (e["o"] == o)]
+
+
+class _ComputeFunctionExtrema:
+    _which = ""
+    _defaults = (0.01, 10.0, 1, 5)
+    _params = dict(first_octave_index=-1, scale_count_per_octave=5)
+
+    def __init__(self, pyramid_params: ImagePyramidParams | None = None, extremum_thres=None, edge_ratio_thres=None,
+                 img_padding_sz=None, extremum_refinement_iter=None, device: int = 0):
+        self.params = pyramid_params or ImagePyramidParams(**self._params)
+        given = (extremum_thres, edge_ratio_thres, img_padding_sz, extremum_refinement_iter)
+        self.args = tuple(d if g is None else g for g, d in zip(given, self._defaults))
+        self.device = device
+        self._ctx = None
+
+    def __call__(self, image):
+        """Returns (extrema, scale_octave_pairs)."""
+        _, w, h, _, _ = _as_image(image)
+        if self._ctx is None:
+            self._ctx = SiftContext(w, h, self.device, min_first_octave_index=min(self.params.first_octave_index, 0))
+        e = self._ctx.function_extrema(self._which, image, self.params, *self.args)
+        return e, np.stack([e["s"], e["o"]], axis=1)
+
+    def gaussians(self, s, o):
+        return self._ctx.gaussian_layer(s, o)
+
+    def _function(self, s, o):
+        return self._ctx.dog_layer(s, o)
+
+
+class ComputeLoGExtrema(_ComputeFunctionExtrema):
+    """DO::Sara::ComputeLoGExtrema (FeatureDetectors/LoG.hpp:71-117): constructor defaults
+    ImagePyramidParams(-1, 3 + 2), 0.01, 10, 1, 5; call operator; laplacians_of_gaussians(s, o)."""
+    _which = "log"
+
+    def laplacians_of_gaussians(self, s, o):
+        return self._function(s, o)
+
+
+class ComputeDoHExtrema(_ComputeFunctionExtrema):
+    """DO::Sara::ComputeDoHExtrema (FeatureDetectors/Hessian.hpp:195-240): constructor defaults
+    ImagePyramidParams(-1, 3 + 2, 2^(1/3), 2), 1e-6, 10, 1, 2; call operator; det_of_hessians(s, o)."""
+    _which = "doh"
+    _defaults = (1e-6, 10.0, 1, 2)
+    _params = dict(first_octave_index=-1, scale_count_per_octave=5, image_padding_size=2)
+
+    def det_of_hessians(self, s, o):
+        return self._function(s, o)
 
 
 _DEFAULT_CTX: dict = {}

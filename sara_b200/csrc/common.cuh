@@ -106,6 +106,10 @@ namespace sb {
   void launch_rgb8_to_gray32f(const uint8_t* src, float* dst, int n_pixels, const double* d_lut, cudaStream_t st);
   void launch_gray8_to_gray32f(const uint8_t* src, float* dst, int n_pixels, cudaStream_t st);
 
+  // Sibling detectors (extrema.cu): fills the D stack of every octave with n_scales function layers,
+  // which = 1: sigma^2 Laplacian, 2: sigma^4 det Hessian; norm[s] is the scale normalisation of layer s.
+  int launch_function_pyramid(const PyramidDesc& P, int which, const float* norm, cudaStream_t st);
+
   struct ExtremaParams
   {
     float extremum_thres;

@@ -63,6 +63,7 @@ namespace {
     std::vector<Taps> stage_taps;  // per scale s >= 1
     bool busy = false;
     bool has_keypoints = false;  // the last frame ran the keypoint stages
+    bool function_pyramid = false;  // the D stack holds a LoG / DoH pyramid (n_scales layers) instead of the DoG
     int classified_upto = 0;     // octaves already classified while the pyramid was still running
     cudaEvent_t ev[9] = {};  // [7], [8]: around the pyramid's longest launch
     double top_kernel_bytes = 0.;
@@ -277,6 +278,9 @@ namespace {
   {
     const int n_s = g.n_scales;
     const int n_ext_layers = std::max(n_s - 3, 0);
+    // Room for the sibling detectors (LoG / DoH: a function pyramid with as many layers as the Gaussian
+    // one, searched on n_s - 2 of them): one more layer in the D stack, one more map layer.
+    const int n_fun_layers = std::max(n_s - 2, 1);
     size_t bytes = 0;
     auto take = [&](size_t n) {
       const size_t off = bytes;
@@ -288,18 +292,19 @@ namespace {
     const size_t off_tmp = g.pre_downscale > 0 ? take(sizeof(float) * w * h) : 0;
     size_t off_G[kMaxOctaves], off_D[kMaxOctaves], off_map[kMaxOctaves];
     int pitch[kMaxOctaves];
-    int n_seg = 0;
+    int n_seg = 0, n_seg_fun = 0;
     for (int o = 0; o < g.n_octaves; ++o)
     {
       pitch[o] = static_cast<int>(align_up(g.ow[o], 32));
       const size_t layer = sizeof(float) * pitch[o] * g.oh[o];
       off_G[o] = take(layer * n_s);
-      off_D[o] = take(layer * std::max(n_s - 1, 1));
-      off_map[o] = take(align_up(g.ow[o], 16) * g.oh[o] * std::max(n_ext_layers, 1));
+      off_D[o] = take(layer * n_s);
+      off_map[o] = take(align_up(g.ow[o], 16) * g.oh[o] * n_fun_layers);
       n_seg += n_ext_layers * g.oh[o];
+      n_seg_fun += n_fun_layers * g.oh[o];
     }
-    const size_t off_rows = take(sizeof(int) * std::max(n_seg, 1));
-    const size_t off_segoff = take(sizeof(int) * std::max(n_seg, 1));
+    const size_t off_rows = take(sizeof(int) * std::max(n_seg_fun, 1));
+    const size_t off_segoff = take(sizeof(int) * std::max(n_seg_fun, 1));
 
     if (bytes > S.arena_bytes)
     {
@@ -1023,6 +1028,7 @@ static int sift_enqueue_impl(sara_b200_ctx* ctx, int slot, const void* image, in
   DeviceGuard guard(ctx->device);
   CU(ctx, guard.err);
   cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : S.own_stream;
+  S.function_pyramid = false;
   if (args->extremum_refinement_iter < 1)  // it becomes img_padding_sz (quirk N1); checked before any launch
     return fail(ctx, SARA_B200_ERR_BAD_ARG,
                 "img_padding_sz must be >= 1 (the 3x3x3 neighbourhood must stay inside the layer)");
@@ -1312,6 +1318,7 @@ int sara_b200_dog_extrema(sara_b200_ctx* ctx, int slot, const float* image, int 
                 "img_padding_sz must be >= 1 (the 3x3x3 neighbourhood must stay inside the layer)");
   const ExtremaParams early{args->extremum_thres, args->edge_ratio_thres, args->img_padding_sz,
                             args->extremum_refinement_iter};
+  S.function_pyramid = false;
   rc = enqueue_pyramid(ctx, S, image, w, h, image_on_device != 0, args->pyramid_params,
                        args->gauss_truncate, st, &early);
   if (rc)
@@ -1325,6 +1332,91 @@ int sara_b200_dog_extrema(sara_b200_ctx* ctx, int slot, const float* image, int 
   if (rc)
     return rc;
   return wait_slot(ctx, S);
+}
+
+// ---- sibling detectors on the same pyramid ------------------------------------
+// ComputeLoGExtrema (FeatureDetectors/LoG.cpp:20-58) and ComputeDoHExtrema
+// (FeatureDetectors/Hessian.cpp:59-98): gaussian_pyramid (default truncation), a function pyramid
+// with as many layers as the Gaussian one -- laplacian_pyramid (GaussianPyramid.hpp:156-178) or
+// det_of_hessian_pyramid (Hessian.hpp:35-57) -- then local_scale_space_extrema on s = 1 .. N - 2
+// with the very kernels of the DoG detector (classify, ordered compaction, refinement).
+static int function_extrema(sara_b200_ctx* ctx, int slot, const float* image, int w, int h, int image_on_device,
+                            int which, const sara_b200_dog_args* args)
+{
+  int rc = check_slot(ctx, slot);
+  if (rc)
+    return rc;
+  if (!image || !args)
+    return fail(ctx, SARA_B200_ERR_BAD_ARG, "null argument");
+  Slot& S = ctx->slots[slot];
+  if (S.busy)
+    return fail(ctx, SARA_B200_ERR_BUSY, "slot %d holds an un-collected frame", slot);
+  if (args->pyramid_params.scale_count_per_octave < 3)
+    return fail(ctx, SARA_B200_ERR_TOO_FEW_SCALES, "scale-space extrema need at least 3 scales per octave");
+  if (args->pyramid_params.scale_count_per_octave + 1 > kMaxScales)
+    return fail(ctx, SARA_B200_ERR_BAD_ARG, "too many scales per octave");
+  if (args->img_padding_sz < 1)
+    return fail(ctx, SARA_B200_ERR_BAD_ARG,
+                "img_padding_sz must be >= 1 (the 3x3x3 neighbourhood must stay inside the layer)");
+  DeviceGuard guard(ctx->device);
+  CU(ctx, guard.err);
+  cudaStream_t st = S.own_stream;
+  S.function_pyramid = false;
+  rc = enqueue_pyramid(ctx, S, image, w, h, image_on_device != 0, args->pyramid_params, 4.f, st, nullptr);
+  if (rc)
+    return rc;
+  // the function pyramid replaces the DoG in the D stack
+  const PyramidDesc& P = S.P;
+  float norm[kMaxScales];
+  for (int s = 0; s < P.n_scales; ++s)
+  {
+    // float(square(scale_relative_to_octave(s))) / float(quartic(...)): powers taken in double
+    const double sr = std::pow(static_cast<double>(args->pyramid_params.scale_geometric_factor), static_cast<double>(s)) *
+                      static_cast<double>(args->pyramid_params.scale_initial);
+    norm[s] = static_cast<float>(which == 1 ? sr * sr : sr * sr * sr * sr);
+  }
+  S.total_launches += launch_function_pyramid(P, which, norm, st);
+  S.function_pyramid = true;
+
+  // the same descriptor with one more "DoG" layer: N function layers, N - 2 of them searched
+  PyramidDesc Pf = P;
+  Pf.n_scales = P.n_scales + 1;
+  const int n_fun = P.n_scales - 2;
+  int seg_base = 0;
+  int* rows0 = P.oct[0].row_count;
+  for (int o = 0; o < P.n_octaves; ++o)
+  {
+    Pf.oct[o].row_count = rows0 + seg_base;
+    Pf.oct[o].seg_base = seg_base;
+    seg_base += n_fun * P.oct[o].h;
+  }
+  CU(ctx, cudaMemsetAsync(S.counters, 0, sizeof(Counters), st));
+  if (P.n_octaves > 0 && seg_base > 0)
+  {
+    ExtremaParams ep{args->extremum_thres, args->edge_ratio_thres, args->img_padding_sz, args->extremum_refinement_iter};
+    S.total_launches += launch_extrema(Pf, ep, seg_base, S.seg_offsets, S.cand, ctx->cap_cand, S.ext_tmp, 0, S.scratch,
+                                       S.ext, ctx->cap_ext, S.counters, st);
+  }
+  if (ctx->profiling)
+    CU(ctx, cudaEventRecord(S.ev[3], st));
+  CU(ctx, cudaGetLastError());
+  S.has_keypoints = false;
+  rc = finish_enqueue(ctx, S, st);
+  if (rc)
+    return rc;
+  return wait_slot(ctx, S);
+}
+
+int sara_b200_log_extrema(sara_b200_ctx* ctx, int slot, const float* image, int w, int h, int image_on_device,
+                          const sara_b200_dog_args* args)
+{
+  return function_extrema(ctx, slot, image, w, h, image_on_device, 1, args);
+}
+
+int sara_b200_doh_extrema(sara_b200_ctx* ctx, int slot, const float* image, int w, int h, int image_on_device,
+                          const sara_b200_dog_args* args)
+{
+  return function_extrema(ctx, slot, image, w, h, image_on_device, 2, args);
 }
 
 int sara_b200_pyramid_enqueue(sara_b200_ctx* ctx, int slot, const float* image, int w, int h,
@@ -1342,6 +1434,7 @@ int sara_b200_pyramid_enqueue(sara_b200_ctx* ctx, int slot, const float* image, 
   DeviceGuard guard(ctx->device);
   CU(ctx, guard.err);
   cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : S.own_stream;
+  S.function_pyramid = false;
   rc = enqueue_pyramid(ctx, S, image, w, h, image_on_device != 0, *params, gauss_truncate, st);
   if (rc)
     return rc;
@@ -1393,7 +1486,7 @@ int sara_b200_copy_layer(sara_b200_ctx* ctx, int slot, int which, int s, int o, 
     return rc;
   Slot& S = ctx->slots[slot];
   const PyramidDesc& P = S.P;
-  if (!dst || o < 0 || o >= P.n_octaves || s < 0 || s >= (which == 0 ? P.n_scales : P.n_scales - 1) ||
+  if (!dst || o < 0 || o >= P.n_octaves || s < 0 || s >= (which == 0 || ctx->slots[slot].function_pyramid ? P.n_scales : P.n_scales - 1) ||
       (which != 0 && which != 1))
     return fail(ctx, SARA_B200_ERR_BAD_ARG, "copy_layer: bad (which=%d, s=%d, o=%d)", which, s, o);  // std::out_of_range in ImagePyramid
   rc = wait_slot(ctx, S);

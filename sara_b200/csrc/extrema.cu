@@ -613,7 +613,87 @@ namespace sb {
         }
     }
 
+    // ---- sibling detectors: function pyramids from the Gaussian pyramid -------------------
+    // which = 1: Laplacian functor (ImageProcessing/Differential.hpp:106-135, borders replicated)
+    //            times float(sigma^2)                  (GaussianPyramid.hpp:156-178)
+    // which = 2: Hessian functor (Differential.hpp:191-226) -> 2 x 2 determinant times float(sigma^4)
+    //            (FeatureDetectors/Hessian.hpp:35-57)
+    struct FunctionNorm
+    {
+      float v[kMaxScales];
+    };
+    template <int WHICH>
+    __global__ void __launch_bounds__(256)
+        function_layers_kernel(const __grid_constant__ PyramidDesc P, int o, const FunctionNorm norm)
+    {
+      const OctaveDesc& oct = P.oct[o];
+      const int w = oct.w, h = oct.h, pitch = oct.pitch;
+      const long long n = static_cast<long long>(w) * h * P.n_scales;
+      for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+           i += static_cast<long long>(gridDim.x) * blockDim.x)
+      {
+        const int x = static_cast<int>(i % w);
+        const int y = static_cast<int>((i / w) % h);
+        const int s = static_cast<int>(i / (static_cast<long long>(w) * h));
+        const float* G = oct.G + static_cast<size_t>(s) * oct.layer_stride;
+        const float c = ld(G, pitch, x, y);
+        float out;
+        if (WHICH == 1)
+        {
+          float value = 0.f;
+          if (x == 0)
+            value = __fadd_rn(value, __fadd_rn(ld(G, pitch, x + 1, y), c));
+          else if (x == w - 1)
+            value = __fadd_rn(value, __fadd_rn(c, ld(G, pitch, x - 1, y)));
+          else
+            value = __fadd_rn(value, __fadd_rn(ld(G, pitch, x + 1, y), ld(G, pitch, x - 1, y)));
+          if (y == 0)
+            value = __fadd_rn(value, __fadd_rn(ld(G, pitch, x, y + 1), c));
+          else if (y == h - 1)
+            value = __fadd_rn(value, __fadd_rn(c, ld(G, pitch, x, y - 1)));
+          else
+            value = __fadd_rn(value, __fadd_rn(ld(G, pitch, x, y + 1), ld(G, pitch, x, y - 1)));
+          out = __fsub_rn(value, __fmul_rn(4.f, c));
+        }
+        else
+        {
+          const float xn = x == w - 1 ? c : ld(G, pitch, x + 1, y), xp = x == 0 ? c : ld(G, pitch, x - 1, y);
+          const float yn = y == h - 1 ? c : ld(G, pitch, x, y + 1), yp = y == 0 ? c : ld(G, pitch, x, y - 1);
+          const float hxx = __fadd_rn(__fsub_rn(xn, __fmul_rn(2.f, c)), xp);
+          const float hyy = __fadd_rn(__fsub_rn(yn, __fmul_rn(2.f, c)), yp);
+          const int nx = x == w - 1 ? 0 : 1, px = x == 0 ? 0 : -1;
+          const int ny = y == h - 1 ? 0 : 1, py = y == 0 ? 0 : -1;
+          const float hxy = __fdiv_rn(
+              __fadd_rn(__fsub_rn(__fsub_rn(ld(G, pitch, x + nx, y + ny), ld(G, pitch, x + px, y + ny)),
+                                  ld(G, pitch, x + nx, y + py)),
+                        ld(G, pitch, x + px, y + py)),
+              4.f);
+          out = __fsub_rn(__fmul_rn(hxx, hyy), __fmul_rn(hxy, hxy));
+        }
+        oct.D[static_cast<size_t>(s) * oct.layer_stride + static_cast<size_t>(y) * pitch + x] = __fmul_rn(out, norm.v[s]);
+      }
+    }
+
   }  // namespace
+
+  int launch_function_pyramid(const PyramidDesc& P, int which, const float* norm, cudaStream_t st)
+  {
+    FunctionNorm fn{};
+    for (int s = 0; s < P.n_scales; ++s)
+      fn.v[s] = norm[s];
+    int launches = 0;
+    for (int o = 0; o < P.n_octaves; ++o)
+    {
+      const long long n = static_cast<long long>(P.oct[o].w) * P.oct[o].h * P.n_scales;
+      const int blocks = static_cast<int>(std::max<long long>(1, std::min<long long>((n + 255) / 256, 148 * 16)));
+      if (which == 1)
+        function_layers_kernel<1><<<blocks, 256, 0, st>>>(P, o, fn);
+      else
+        function_layers_kernel<2><<<blocks, 256, 0, st>>>(P, o, fn);
+      ++launches;
+    }
+    return launches;
+  }
 
   // Classifies octaves [o_lo, o_hi).  The row counters of ALL octaves are zeroed when
   // `zero_counts` is set (they are contiguous, starting at octave 0's).

@@ -231,3 +231,26 @@ def test_quirk_minima_never_refined():
     assert np.array_equal(mins["y"], mins["yi"].astype(np.float32))
     maxs = e[e["extremum_type"] == 1]
     assert np.any(maxs["x"] != maxs["xi"].astype(np.float32))
+
+
+def test_log_detector_reference_kat():
+    """cpp/test/Sara/FeatureDetectors/test_featuredetectors_log.cpp:24-78: a 5 x 5 block of ones in an 11 x 11
+    image, ImagePyramidParams(0, 6, 2^(1/3), 1, 1, 1.6): the first LoG extremum sits at the block centre."""
+    N = 11
+    img = np.zeros((N, N), np.float32)
+    img[3:8, 3:8] = 1
+    pp = O.PyramidParams(0, 6, float(np.float32(2.0) ** np.float32(1.0 / 3.0)), 1, 1.0, 1.6)
+    r = O.compute_function_extrema(img, "log", pp)
+    e = r.extrema
+    assert len(e) >= 1
+    z = r.octave_scaling(int(e[0]["o"]))
+    assert abs(e[0]["x"] * z - 5) < 1e-2 and abs(e[0]["y"] * z - 5) < 1e-2
+
+
+def test_doh_detector_reference_smoke():
+    """test_featuredetectors_hessian.cpp:35-46: default ComputeDoHExtrema on a single bright pixel runs."""
+    img = np.zeros((21, 21), np.float32)
+    img[1, 1] = 1
+    r = O.compute_function_extrema(img, "doh", O.PyramidParams(-1, 5, float(np.float32(2.0) ** np.float32(1.0 / 3.0)), 2),
+                                   1e-6, 10.0, 1, 2)
+    assert r.num_octaves >= 1 and r.num_scales == 5
