@@ -267,6 +267,20 @@ SARA_B200_API int sara_b200_copy_extrema(sara_b200_ctx* ctx, int slot, sara_b200
 SARA_B200_API int sara_b200_copy_oriented(sara_b200_ctx* ctx, int slot, sara_b200_keypoint* dst, int capacity,
                             int* n_out);
 
+/* ---- stage functors on caller-supplied extrema ---------------------------------
+ * ComputeDominantOrientations::operator() (FeatureDescriptors/Orientation.hpp:233-242,
+ * Orientation.cpp:135-166) and ComputeSIFTDescriptor<4, 8>::operator()
+ * (FeatureDescriptors/SIFT.hpp:62-166) + the rescale of SIFT.cpp:92-98, run on `n` extrema
+ * the caller supplies (host array; x, y, shape, extremum fields and the (s, o) pair of
+ * `scale_octave_pairs`, octave coordinates) against the Gaussian pyramid the slot holds.
+ * Outputs (host, each may be NULL): `oriented` -- one copy of the extremum per dominant
+ * orientation, octave coordinates, extrema without a peak dropped, order kept;
+ * `keypoints` / `descriptors` -- the same rows rescaled to image coordinates and their
+ * 128-float descriptors.  *n_out = number of oriented keypoints. */
+SARA_B200_API int sara_b200_describe_extrema(sara_b200_ctx* ctx, int slot, const sara_b200_keypoint* extrema, int n,
+                               sara_b200_keypoint* oriented, sara_b200_keypoint* keypoints,
+                               float* descriptors, int capacity, int* n_out);
+
 /* ---- building blocks exposed for unit parity (same semantics as the
  * reference functions named) --------------------------------------------------
  * gaussian(): LinearFiltering.hpp:446-454 / LinearFiltering.cpp:30-68;

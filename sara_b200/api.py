@@ -113,7 +113,7 @@ SYMBOLS = [
     "sara_b200_make_gaussian_kernel", "sara_b200_sift_u8", "sara_b200_sift_enqueue_u8", "sara_b200_to_gray32f",
     "sara_b200_collect_device", "sara_b200_set_graphs",
     "sara_b200_default_match_args", "sara_b200_knn", "sara_b200_compute_matches",
-    "sara_b200_log_extrema", "sara_b200_doh_extrema",
+    "sara_b200_log_extrema", "sara_b200_doh_extrema", "sara_b200_describe_extrema",
 ]
 
 
@@ -160,6 +160,7 @@ def load_library() -> C.CDLL:
     L.sara_b200_dog_extrema.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.POINTER(_DogArgs)]
     L.sara_b200_log_extrema.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.POINTER(_DogArgs)]
     L.sara_b200_doh_extrema.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.POINTER(_DogArgs)]
+    L.sara_b200_describe_extrema.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp, vp, C.c_int, ip]
     L.sara_b200_pyramid_enqueue.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.POINTER(_PyrParams), C.c_float, vp]
     L.sara_b200_num_octaves.argtypes = [vp, C.c_int]
     L.sara_b200_num_scales.argtypes = [vp, C.c_int]
@@ -487,6 +488,25 @@ class SiftContext:
         self._check(fn(self._ctx, slot, ptr, w, h, int(on_dev), C.byref(args)))
         del keep
         return self.extrema(slot)
+
+    def describe_extrema(self, extrema, slot=0):
+        """ComputeDominantOrientations + ComputeSIFTDescriptor<4, 8> (+ rescale) on the given extrema against the
+        pyramid the slot holds.  Returns (oriented keypoints in octave coordinates, KeypointList in image
+        coordinates)."""
+        e = np.ascontiguousarray(extrema, dtype=KEYPOINT_DTYPE)
+        cap = max(4 * len(e), 16)
+        while True:
+            ori = np.empty(cap, KEYPOINT_DTYPE)
+            kps = np.empty(cap, KEYPOINT_DTYPE)
+            desc = np.empty((cap, 128), np.float32)
+            n = C.c_int(0)
+            rc = self._L.sara_b200_describe_extrema(self._ctx, slot, e.ctypes.data, len(e), ori.ctypes.data,
+                                                    kps.ctypes.data, desc.ctypes.data, cap, C.byref(n))
+            if rc == -5 and n.value > cap:
+                cap = n.value
+                continue
+            self._check(rc)
+            return ori[: n.value].copy(), KeypointList(kps[: n.value].copy(), desc[: n.value].copy())
 
     # ---- stage accessors -----------------------------------------------------------------
     def num_octaves(self, slot=0) -> int:

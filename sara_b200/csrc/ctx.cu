@@ -1524,6 +1524,76 @@ int sara_b200_copy_oriented(sara_b200_ctx* ctx, int slot, sara_b200_keypoint* ds
   return copy_keypoints(ctx, S, S.kp_oct, n, ctx->cap_kp, dst, capacity, n_out);
 }
 
+// ---- stage functors on caller-supplied extrema ---------------------------------------------
+// ComputeDominantOrientations::operator() (FeatureDescriptors/Orientation.hpp:233-242,
+// Orientation.cpp:135-166) followed -- when `descriptors` is asked for -- by
+// ComputeSIFTDescriptor<4, 8>::operator() (FeatureDescriptors/SIFT.hpp:62-166) and the rescale of
+// SIFT.cpp:92-98, on the Gaussian pyramid the slot holds (after sara_b200_dog_extrema,
+// sara_b200_pyramid_enqueue + wait, or a whole sift call).
+int sara_b200_describe_extrema(sara_b200_ctx* ctx, int slot, const sara_b200_keypoint* extrema, int n,
+                               sara_b200_keypoint* oriented, sara_b200_keypoint* keypoints, float* descriptors,
+                               int capacity, int* n_out)
+{
+  int rc = check_slot(ctx, slot);
+  if (rc)
+    return rc;
+  Slot& S = ctx->slots[slot];
+  rc = wait_slot(ctx, S);
+  if (rc)
+    return rc;
+  if (n_out)
+    *n_out = 0;
+  if (n < 0 || (n > 0 && !extrema) || capacity < 0)
+    return fail(ctx, SARA_B200_ERR_BAD_ARG, "describe_extrema: bad arguments");
+  if (S.P.n_octaves <= 0)
+    return fail(ctx, SARA_B200_ERR_BAD_ARG, "describe_extrema: the slot holds no Gaussian pyramid");
+  if (n > ctx->cap_ext)
+    return fail(ctx, SARA_B200_ERR_OVERFLOW, "%d extrema exceed the context capacity %d", n, ctx->cap_ext);
+  for (int i = 0; i < n; ++i)  // the (s, o) pair of every extremum (scale_octave_pairs) must address a layer
+    if (extrema[i].o < 0 || extrema[i].o >= S.P.n_octaves || extrema[i].s < 0 || extrema[i].s >= S.P.n_scales)
+      return fail(ctx, SARA_B200_ERR_BAD_ARG, "describe_extrema: extremum %d has (s, o) = (%d, %d) outside the pyramid",
+                  i, extrema[i].s, extrema[i].o);
+  DeviceGuard guard(ctx->device);
+  CU(ctx, guard.err);
+  cudaStream_t st = S.own_stream;
+  S.stream = st;
+  Counters zero{};
+  zero.n_ext = n;
+  CU(ctx, cudaMemcpyAsync(S.counters, &zero, sizeof(Counters), cudaMemcpyHostToDevice, st));
+  if (n > 0)
+    CU(ctx, cudaMemcpyAsync(S.ext, extrema, sizeof(Keypoint) * n, cudaMemcpyHostToDevice, st));
+  const bool prof = ctx->profiling;
+  ctx->profiling = false;  // the stage events of a whole frame do not apply here
+  rc = enqueue_describe(ctx, S, st);
+  ctx->profiling = prof;
+  if (rc)
+    return rc;
+  S.has_keypoints = true;
+  rc = finish_enqueue(ctx, S, st);
+  if (rc)
+    return rc;
+  CU(ctx, cudaStreamSynchronize(st));
+  S.busy = false;
+  const Counters c = *S.h_counters;
+  if (n_out)
+    *n_out = c.n_kp;
+  if (c.overflow || c.n_kp > ctx->cap_kp)
+    return fail(ctx, SARA_B200_ERR_OVERFLOW, "%d oriented keypoints exceed the context capacity %d", c.n_kp, ctx->cap_kp);
+  if (c.n_kp > capacity)
+    return fail(ctx, SARA_B200_ERR_OVERFLOW, "%d keypoints exceed the caller's capacity %d", c.n_kp, capacity);
+  if (c.n_kp > 0)
+  {
+    if (oriented)
+      CU(ctx, cudaMemcpyAsync(oriented, S.kp_oct, sizeof(Keypoint) * c.n_kp, cudaMemcpyDeviceToHost, st));
+    if (keypoints)
+      CU(ctx, cudaMemcpyAsync(keypoints, S.kp_out, sizeof(Keypoint) * c.n_kp, cudaMemcpyDeviceToHost, st));
+    if (descriptors)
+      CU(ctx, cudaMemcpyAsync(descriptors, S.desc, sizeof(float) * 128 * c.n_kp, cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+  }
+  return 0;
+}
+
 int sara_b200_gaussian(sara_b200_ctx* ctx, const float* src, int w, int h, float sigma, float gauss_truncate,
                        float* dst)
 {

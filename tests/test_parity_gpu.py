@@ -353,3 +353,33 @@ def test_many_slots_mixed_sizes_repeatable():
                 assert kl.descriptors.tobytes() == single[slot].descriptors.tobytes()
     finally:
         c.close()
+
+
+def test_stage_functors_on_supplied_extrema():
+    """ComputeDominantOrientations / ComputeSIFTDescriptor entry point: the extrema of ComputeDoGExtrema handed
+    back by the caller give exactly the keypoints and descriptors of the whole compute_sift_keypoints call;
+    a subset gives the matching subset; a bad (s, o) pair is rejected."""
+    img = S.tex(800, 600, 4321)
+    ctx = sb.SiftContext(800, 600, device=0)
+    pp = sb.ImagePyramidParams(first_octave_index=0)
+    kl = ctx.compute_sift_keypoints(img, pp)
+    ext = ctx.extrema()
+    # N1: compute_sift_keypoints passes its refinement-iteration argument as the padding
+    e2 = ctx.dog_extrema(img, pp, 4.0, 0.01, 10.0, 5, 5)
+    assert e2.tobytes() == ext.tobytes()
+    ori, kl2 = ctx.describe_extrema(e2)
+    assert len(kl2) == len(kl) > 300
+    assert kl2.features.tobytes() == kl.features.tobytes()
+    assert kl2.descriptors.tobytes() == kl.descriptors.tobytes()
+    assert np.array_equal(ori["orientation"], kl.features["orientation"])
+    sub = e2[::7]
+    _, kl3 = ctx.describe_extrema(sub)
+    keep = np.isin(kl.features["xi"] * 100000 + kl.features["yi"] + 1e7 * kl.features["s"] + 1e8 * kl.features["o"],
+                   sub["xi"] * 100000 + sub["yi"] + 1e7 * sub["s"] + 1e8 * sub["o"])
+    assert kl3.descriptors.tobytes() == kl.descriptors[keep].tobytes()
+    bad = e2[:3].copy()
+    bad["o"][1] = 99
+    with pytest.raises(ValueError):
+        ctx.describe_extrema(bad)
+    assert len(ctx.describe_extrema(e2[:0])[1]) == 0
+    ctx.close()
