@@ -249,7 +249,7 @@ namespace sb {
     // the grid: a cheap geometric test runs on all pixels, the survivors are compacted through a
     // small per-warp queue (ballot + popc), and the expensive part (gradient, atan2, exp,
     // trilinear update of 8 bins) runs on full warps.
-    __global__ void __launch_bounds__(DESC_WARPS * 32)
+    __global__ void __launch_bounds__(DESC_WARPS * 32, 5)
         descriptor_kernel(const __grid_constant__ PyramidDesc P, const Keypoint* __restrict__ kp_oct,
                           Counters* __restrict__ counters, int cap_kp, Keypoint* __restrict__ kp_out,
                           float* __restrict__ desc)
@@ -421,62 +421,76 @@ namespace sb {
           }
         };
 
-        const int side = 2 * rounded_r + 1;
-        const int count = side * side;
+        // The kept pixels of the bounding square [-rounded_r, rounded_r]^2, in raster order.  The test of
+        // SIFT.hpp:84-110 (-1 < pos < 4 on both axes, pos = T (u, v) + 1.5) is linear in u, so on a row the
+        // kept pixels form one interval: a lane works out the interval of one row from the inverse
+        // inequalities, widened by a pixel on both sides (the exact float test below has the last word),
+        // and the warp then visits only those pixels -- about half of the square -- 32 at a time.
         int q_n = 0;  // entries waiting in the queue (< 96 between rounds)
-        // lane's pixel of the bounding square, advanced by 32 per round.  `side` can be smaller
-        // than a warp (refined sigma < 1.46 <=> rounded_r <= 15), so wrapping takes a loop.
-        int u = lane - rounded_r, v = -rounded_r;
-        while (u > rounded_r)
+        const int u_min = max(-rounded_r, -rx), u_max = min(rounded_r, w - 1 - rx);
+        for (int v0 = -rounded_r; v0 <= rounded_r; v0 += 32)
         {
-          u -= side;
-          ++v;
-        }
-        for (int t0 = 0; t0 < count; t0 += 32)
-        {
-          const int t = t0 + lane;
-          bool keep = false;
-          int uv = 0;
-          if (t < count)
+          int my_lo = 1, my_hi = 0;  // empty
           {
-            const int X = rx + u, Y = ry + v;
-            const float fu = static_cast<float>(u), fv = static_cast<float>(v);
-            const float px = __fadd_rn(__fadd_rn(__fmul_rn(T00, fu), __fmul_rn(T01, fv)), 1.5f);
-            const float py = __fadd_rn(__fadd_rn(__fmul_rn(T10, fu), __fmul_rn(T11, fv)), 1.5f);
-            keep = X >= 0 && X < w && Y >= 0 && Y < h && fminf(px, py) > -1.f && fmaxf(px, py) < 4.f;
-            uv = (u & 0xffff) | (v << 16);
-          }
-          u += 32;
-          if (side >= 32)  // warp-uniform: the usual case, a single wrap
-          {
-            const bool wrap = u > rounded_r;
-            u -= wrap ? side : 0;
-            v += wrap ? 1 : 0;
-          }
-          else
-          {
-            while (u > rounded_r)
+            const int v = v0 + lane, Y = ry + v;
+            if (v <= rounded_r && Y >= 0 && Y < h)
             {
-              u -= side;
-              ++v;
+              const float fv = static_cast<float>(v);
+              const float bx = __fmul_rn(T01, fv) + 1.5f, by = __fmul_rn(T11, fv) + 1.5f;
+              float lo = -1e9f, hi = 1e9f;
+              if (fabsf(T00) > 1e-12f)
+              {
+                const float e0 = (-1.f - bx) / T00, e1 = (4.f - bx) / T00;
+                lo = fmaxf(lo, fminf(e0, e1));
+                hi = fminf(hi, fmaxf(e0, e1));
+              }
+              if (fabsf(T10) > 1e-12f)
+              {
+                const float e0 = (-1.f - by) / T10, e1 = (4.f - by) / T10;
+                lo = fmaxf(lo, fminf(e0, e1));
+                hi = fminf(hi, fmaxf(e0, e1));
+              }
+              lo = fmaxf(lo, -70000.f);
+              hi = fminf(hi, 70000.f);
+              if (lo <= hi)
+              {
+                my_lo = max(u_min, static_cast<int>(floorf(lo)) - 1);
+                my_hi = min(u_max, static_cast<int>(ceilf(hi)) + 1);
+              }
             }
           }
-          const unsigned m = __ballot_sync(0xffffffffu, keep);
-          if (keep)
-            queue[q_n + __popc(m & ((1u << lane) - 1u))] = uv;
-          q_n += __popc(m);
-          __syncwarp();
-          if (q_n >= 96)
+          const int n_rows = min(32, rounded_r - v0 + 1);
+          for (int rrow = 0; rrow < n_rows; ++rrow)
           {
-            drain(96);
-            // move the leftover (< 32 entries) to the front
-            const int rest = q_n - 96;
-            const int moved = lane < rest ? queue[96 + lane] : 0;
-            __syncwarp();
-            if (lane < rest)
-              queue[lane] = moved;
-            q_n = rest;
-            __syncwarp();
+            const int ulo = __shfl_sync(0xffffffffu, my_lo, rrow), uhi = __shfl_sync(0xffffffffu, my_hi, rrow);
+            const int v = v0 + rrow;
+            const float fv = static_cast<float>(v);
+            const float tx = __fmul_rn(T01, fv), ty = __fmul_rn(T11, fv);
+            for (int ub = ulo; ub <= uhi; ub += 32)
+            {
+              const int u = ub + lane;
+              const float fu = static_cast<float>(u);
+              const float px = __fadd_rn(__fadd_rn(__fmul_rn(T00, fu), tx), 1.5f);
+              const float py = __fadd_rn(__fadd_rn(__fmul_rn(T10, fu), ty), 1.5f);
+              const bool keep = u <= uhi && fminf(px, py) > -1.f && fmaxf(px, py) < 4.f;
+              const unsigned m = __ballot_sync(0xffffffffu, keep);
+              if (keep)
+                queue[q_n + __popc(m & ((1u << lane) - 1u))] = (u & 0xffff) | (v << 16);
+              q_n += __popc(m);
+              __syncwarp();
+              if (q_n >= 96)
+              {
+                drain(96);
+                // move the leftover (< 32 entries) to the front
+                const int rest = q_n - 96;
+                const int moved = lane < rest ? queue[96 + lane] : 0;
+                __syncwarp();
+                if (lane < rest)
+                  queue[lane] = moved;
+                q_n = rest;
+                __syncwarp();
+              }
+            }
           }
         }
         drain(q_n);

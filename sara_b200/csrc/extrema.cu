@@ -46,6 +46,7 @@ namespace sb {
     {
       int base[kMaxOctaves + 1];  // first warp of every octave
       int n_cb[kMaxOctaves];      // column blocks of the octave
+      int seg;                    // rows a warp classifies
     };
 
     __device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
@@ -113,7 +114,7 @@ namespace sb {
       const int sg = local / Tl.n_cb[o], cb = local - sg * Tl.n_cb[o];
       const int w = oct.w, h = oct.h, pitch = oct.pitch;
       const int x0 = CLS_W * cb - 4 + 4 * lane;  // first of the lane's four pixels
-      const int ya = sg * CLS_SEG, yb = min(ya + CLS_SEG, h);
+      const int ya = sg * Tl.seg, yb = min(ya + Tl.seg, h);
       const bool ld_on = x0 >= 0 && x0 < w;      // the 16-byte load stays inside the padded row
       const bool out_on = lane >= 1 && lane <= 30 && x0 < w;
       const float thr = __fmul_rn(0.8f, ep.extremum_thres);
@@ -716,11 +717,18 @@ namespace sb {
       return launches;
     }
     ClassifyTiles T{};
+    // A launch that covers octave 0 fills the machine with 32-row segments; the smaller octaves alone are a
+    // latency-bound launch (a warp walks its rows one after the other) and get short segments instead.
+    static const int seg_small = [] {
+      const char* e = getenv("SARA_B200_CLS_SEG_SMALL");
+      return e ? std::max(4, atoi(e)) : 8;
+    }();
+    T.seg = o_lo == 0 ? CLS_SEG : seg_small;
     for (int o = 0; o < P.n_octaves; ++o)
     {
       const bool in = o >= o_lo && o < o_hi;
       T.n_cb[o] = (P.oct[o].w + CLS_W - 1) / CLS_W;
-      const int n_sg = (P.oct[o].h + CLS_SEG - 1) / CLS_SEG;
+      const int n_sg = (P.oct[o].h + T.seg - 1) / T.seg;
       T.base[o + 1] = T.base[o] + (in ? T.n_cb[o] * n_sg : 0);
     }
     if (T.base[P.n_octaves] == 0)
