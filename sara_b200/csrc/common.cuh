@@ -98,6 +98,8 @@ namespace sb {
                     int pitch, int nw, int nh, int npitch, const Taps& taps, cudaStream_t st);
   bool downscale_is_even_sampling(int sw, int sh, int dw, int dh);
   // All octaves from `first_octave` on in one single-CTA launch (pyramid.cu); 0 if not applicable.
+  // Scales 1 and 2 of a small octave in one launch (pyramid.cu); false if the schedule is not the default one.
+  bool launch_octave_head(const OctaveDesc& oc, const OctaveDesc* next, const Taps& t1, const Taps& t2, cudaStream_t st);
   int launch_tail_octaves(const PyramidDesc& P, int first_octave, int downscale_index, const Taps* taps,
                           cudaStream_t st);
 

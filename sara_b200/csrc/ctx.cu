@@ -26,14 +26,17 @@ namespace {
 
   thread_local char g_create_error[512] = "";
 
+  // One side stream per octave after the first (octave o runs on side[o - 1]; beyond kNumSide they wrap).
+  constexpr int kNumSide = 8;
+
   struct Slot
   {
     cudaStream_t own_stream = nullptr;
     // Octaves overlap: octave o + 1 only needs scale `downscale_index` of octave o, so the octaves
     // run on alternating side streams chained by events and are joined back at the end.
-    cudaStream_t side[3] = {};
+    cudaStream_t side[kNumSide] = {};
     cudaEvent_t ev_down[kMaxOctaves] = {};
-    cudaEvent_t ev_join[3] = {};
+    cudaEvent_t ev_join[kNumSide] = {};
     cudaStream_t stream = nullptr;  // stream of the frame in flight
     // pyramid arena (grown on demand)
     char* arena = nullptr;
@@ -514,7 +517,7 @@ namespace {
       const auto launch_inc = marched ? launch_march : launch_stage;
       staged = staged || marched;
       const cudaStream_t main_st = st;
-      bool side_used[3] = {false, false, false};
+      bool side_used[kNumSide] = {};
       for (int o = 0; o < P.n_octaves; ++o)
       {
         const OctaveDesc& oc = P.oct[o];
@@ -523,12 +526,16 @@ namespace {
         {
           // Octave o starts as soon as its base exists (event recorded below, after the launch
           // that wrote it) and runs beside the remaining scales of the octaves above it.
-          st = S.side[(o - 1) % 3];
-          side_used[(o - 1) % 3] = true;
+          st = S.side[(o - 1) % kNumSide];
+          side_used[(o - 1) % kNumSide] = true;
           CU(ctx, cudaStreamWaitEvent(st, S.ev_down[o - 1], 0));
         }
         // The small octaves at the end of the pyramid run in one single-CTA launch.
-        if (mode != SARA_B200_PYRAMID_GENERIC && o > 0 && oc.w * oc.h <= 4096)
+        static const int tail_px = [] {
+          const char* e = getenv("SARA_B200_TAIL_PIXELS");
+          return e ? atoi(e) : 4096;
+        }();
+        if (mode != SARA_B200_PYRAMID_GENERIC && o > 0 && oc.w * oc.h <= tail_px)
         {
           const int n = launch_tail_octaves(P, o, S.downscale_index, S.stage_taps.data(), st);
           if (n > 0)
@@ -541,7 +548,22 @@ namespace {
         {
           const bool fuse_down = next != nullptr && S.downscale_index >= 1 &&
                                  downscale_is_even_sampling(oc.w, oc.h, next->w, next->h);
-          for (int s = 1; s < P.n_scales; ++s)
+          int s_first = 1;
+          // Octaves that cannot fill the machine: scales 1 and 2 -- all that the next octave waits for --
+          // in one launch (octave_head_kernel), the remaining scales as usual.
+          static const int head_px = [] {
+            const char* e = getenv("SARA_B200_HEAD_PIXELS");
+            return e ? atoi(e) : 600000;
+          }();
+          if (o > 0 && oc.w * oc.h <= head_px && P.n_scales >= 3 && S.downscale_index == 2 && (fuse_down || !next) &&
+              launch_octave_head(oc, next, S.stage_taps[1], S.stage_taps[2], st))
+          {
+            ++S.pyramid_launches;
+            if (next)
+              CU(ctx, cudaEventRecord(S.ev_down[o], st));
+            s_first = 3;
+          }
+          for (int s = s_first; s < P.n_scales; ++s)
           {
             const bool down = fuse_down && s == S.downscale_index;
             // The launch with the most taps on the largest octave is the pyramid's longest kernel.
@@ -625,7 +647,7 @@ namespace {
       }
       // join the side streams back into the frame's stream
       st = main_st;
-      for (int i = 0; i < 3; ++i)
+      for (int i = 0; i < kNumSide; ++i)
         if (side_used[i])
         {
           CU(ctx, cudaEventRecord(S.ev_join[i], S.side[i]));
@@ -816,9 +838,20 @@ int sara_b200_create(int device, const sara_b200_limits* limits, sara_b200_ctx**
   for (Slot& S : ctx->slots)
   {
     cudaError_t err = cudaStreamCreateWithFlags(&S.own_stream, cudaStreamNonBlocking);
-    for (int i = 0; i < 3 && err == cudaSuccess; ++i)
+    // The smaller an octave, the shorter its launches and the longer the chain that still hangs on it
+    // (octave o + 1 waits for scale 2 of octave o): the side streams get rising priorities, so that a
+    // small octave's CTAs take the slots that free up before the big octaves' next launches do.
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // numerically lower = more urgent
+    static const int use_prio = [] {
+      const char* e = getenv("SARA_B200_SIDE_PRIORITY");
+      return e ? atoi(e) : 1;
+    }();
+    for (int i = 0; i < kNumSide && err == cudaSuccess; ++i)
     {
-      err = cudaStreamCreateWithFlags(&S.side[i], cudaStreamNonBlocking);
+      const int prio = std::max(prio_hi, prio_lo - (i + 1));
+      err = use_prio ? cudaStreamCreateWithPriority(&S.side[i], cudaStreamNonBlocking, prio)
+                     : cudaStreamCreateWithFlags(&S.side[i], cudaStreamNonBlocking);
       if (err == cudaSuccess)
         err = cudaEventCreateWithFlags(&S.ev_join[i], cudaEventDisableTiming);
     }

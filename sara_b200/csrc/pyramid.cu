@@ -153,7 +153,7 @@ namespace sb {
     // next octave's base is sub-sampled from scale `down` on the way.  Same arithmetic as
     // gaussian_stage_kernel (separate multiply and add, left to right from 0).
     constexpr int TAIL_NT = 1024;
-    constexpr int TAIL_MAX_PIXELS = 4096;  // larger octaves are faster on the multi-CTA stage kernel
+    constexpr int TAIL_MAX_PIXELS = 12288;  // shared-memory limit; the caller decides from which octave on (ctx.cu)
     constexpr int TAIL_MAX_TAPS = 32;
     constexpr int TAIL_MAX_SCALES = 8;
 
@@ -173,15 +173,14 @@ namespace sb {
     {
       const int K = KT > 0 ? KT : k_runtime;
       const int c = K / 2;
-      const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
       float kr[KT > 0 ? KT : 1];  // taps in registers (the parameter bank is slow to index)
 #pragma unroll
       for (int j = 0; j < (KT > 0 ? KT : 1); ++j)
         kr[j] = k[j];
-      for (int y = ty; y < h; y += TAIL_NT / 32)
-       for (int x = tx; x < w; x += 32)
+      // flat pixel index: a 60 x 33 octave takes 2 rounds of the 1024 threads, not 2 x 2
+      for (int i = threadIdx.x; i < w * h; i += TAIL_NT)
       {
-        const int i = y * w + x;
+        const int y = i / w, x = i - y * w;
         const float* row = A + y * w;
         float sum = 0.f;
         if (x >= c && x + c < w)
@@ -215,10 +214,9 @@ namespace sb {
         B[i] = sum;
       }
       __syncthreads();
-      for (int y = ty; y < h; y += TAIL_NT / 32)
-       for (int x = tx; x < w; x += 32)
+      for (int i = threadIdx.x; i < w * h; i += TAIL_NT)
       {
-        const int i = y * w + x;
+        const int y = i / w, x = i - y * w;
         float sum = 0.f;
         if (y >= c && y + c < h)
         {
@@ -310,7 +308,193 @@ namespace sb {
       }
     }
 
+    // ---- scales 1 and 2 of a small octave in ONE launch ("head" of the octave) --------------------
+    // Octave o + 1 starts from scale 2 of octave o, so from the second octave on the pyramid is a
+    // chain of short, strictly dependent launches: two per octave before the next one can start.
+    // For the octaves that cannot fill the machine anyway this kernel does both in one launch:
+    // a CTA owns a 64 x 32 tile and recomputes the 11 / 6 pixel halo of the intermediate images
+    // in shared memory (G0 tile -> row pass -> G1 -> row pass -> G2), writes G(1), D(0), G(2),
+    // D(1) and the sub-sampled base of the next octave.  Arithmetic contract as everywhere:
+    // acc = RN(acc + RN(v * k[j])), j ascending; every pass replicates the border OF THE IMAGE
+    // (LinearFiltering.hpp:95-100, 137-142): intermediates exist only at image positions and are
+    // addressed through clamped coordinates.
+    constexpr int HD_NT = 1024;
+
+    template <int K1, int K2, int TW, int TH>
+    struct HeadGeom
+    {
+      static constexpr int c1 = K1 / 2, c2 = K2 / 2;
+      static constexpr int w_g1 = TW + 2 * c2, h_g1 = TH + 2 * c2;   // G1 region
+      static constexpr int w_r1 = w_g1, h_r1 = h_g1 + 2 * c1;         // row-filtered G0
+      static constexpr int w_g0 = w_g1 + 2 * c1, h_g0 = h_r1;         // G0 region
+      static constexpr int w_r2 = TW, h_r2 = h_g1;                    // row-filtered G1
+      static constexpr int n_g0 = w_g0 * h_g0, n_r1 = w_r1 * h_r1, n_g1 = w_g1 * h_g1, n_r2 = w_r2 * h_r2;
+      static constexpr int smem_floats = n_g0 + n_r1 + n_g1 + n_r2;
+    };
+
+    struct HeadParams
+    {
+      const float* G0;
+      float *G1, *G2, *D0, *D1, *nextG;
+      int w, h, pitch, nw, nh, npitch;
+      float k1[16], k2[16];
+    };
+
+    // EDGE = false: the whole G0 region of the tile lies inside the image, no coordinate is clamped.
+    template <int K1, int K2, int TW, int TH, bool EDGE>
+    __device__ __forceinline__ void head_tile(const HeadParams& p, float* hs, int x0, int y0)
+    {
+      using Gm = HeadGeom<K1, K2, TW, TH>;
+      constexpr int c1 = Gm::c1, c2 = Gm::c2;
+      float* g0 = hs;
+      float* r1 = g0 + Gm::n_g0;
+      float* g1 = r1 + Gm::n_r1;
+      float* r2 = g1 + Gm::n_g1;
+      const int tid = threadIdx.x;
+      const int w = p.w, h = p.h;
+      float k1[K1], k2[K2];
+#pragma unroll
+      for (int j = 0; j < K1; ++j)
+        k1[j] = p.k1[j];
+#pragma unroll
+      for (int j = 0; j < K2; ++j)
+        k2[j] = p.k2[j];
+      auto cx = [&](int x) { return EDGE ? min(max(x, 0), w - 1) : x; };
+      auto cy = [&](int y) { return EDGE ? min(max(y, 0), h - 1) : y; };
+
+      // G0 tile: origin (x0 - c2 - c1, y0 - c2 - c1), clamped reads = the replicated border of the image
+      const int gx0 = x0 - c2 - c1, gy0 = y0 - c2 - c1;
+      for (int i = tid; i < Gm::n_g0; i += HD_NT)
+      {
+        const int ty = i / Gm::w_g0, tx = i - ty * Gm::w_g0;
+        g0[i] = p.G0[static_cast<size_t>(cy(gy0 + ty)) * p.pitch + cx(gx0 + tx)];
+      }
+      __syncthreads();
+      // R1 (row pass of scale 1): columns x0 - c2 .., rows y0 - c2 - c1 ..  A tile position holds the value AT
+      // THE CLAMPED image position; for an in-image x the window reads clamp(x - c1 + j).
+      const int rx0 = x0 - c2, ry0 = gy0;
+      for (int i = tid; i < Gm::n_r1; i += HD_NT)
+      {
+        const int ty = i / Gm::w_r1, tx = i - ty * Gm::w_r1;
+        const int x = cx(rx0 + tx);
+        const float* row = g0 + ty * Gm::w_g0;
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < K1; ++j)
+          acc = __fadd_rn(acc, __fmul_rn(row[cx(x - c1 + j) - gx0], k1[j]));
+        r1[i] = acc;
+      }
+      __syncthreads();
+      // G1 (column pass of scale 1): region origin (x0 - c2, y0 - c2)
+      const int ax0 = x0 - c2, ay0 = y0 - c2;
+      for (int i = tid; i < Gm::n_g1; i += HD_NT)
+      {
+        const int ty = i / Gm::w_g1, tx = i - ty * Gm::w_g1;
+        const int y = cy(ay0 + ty);
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < K1; ++j)
+          acc = __fadd_rn(acc, __fmul_rn(r1[(cy(y - c1 + j) - ry0) * Gm::w_r1 + tx], k1[j]));
+        g1[i] = acc;
+        const int X = ax0 + tx, Y = ay0 + ty;
+        if (X >= x0 && X < min(x0 + TW, w) && Y >= y0 && Y < min(y0 + TH, h))
+        {
+          const size_t g = static_cast<size_t>(Y) * p.pitch + X;
+          p.G1[g] = acc;
+          p.D0[g] = __fsub_rn(acc, g0[(Y - gy0) * Gm::w_g0 + (X - gx0)]);
+        }
+      }
+      __syncthreads();
+      // R2 (row pass of scale 2): columns x0 .., rows y0 - c2 ..
+      for (int i = tid; i < Gm::n_r2; i += HD_NT)
+      {
+        const int ty = i / Gm::w_r2, tx = i - ty * Gm::w_r2;
+        const int x = cx(x0 + tx);
+        const float* row = g1 + ty * Gm::w_g1;
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < K2; ++j)
+          acc = __fadd_rn(acc, __fmul_rn(row[cx(x - c2 + j) - ax0], k2[j]));
+        r2[i] = acc;
+      }
+      __syncthreads();
+      // G2 (column pass of scale 2), D1, next octave
+      for (int i = tid; i < TW * TH; i += HD_NT)
+      {
+        const int ty = i / TW, tx = i - ty * TW;
+        const int X = x0 + tx, Y = y0 + ty;
+        if (X >= w || Y >= h)
+          continue;
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < K2; ++j)
+          acc = __fadd_rn(acc, __fmul_rn(r2[(cy(Y - c2 + j) - ay0) * Gm::w_r2 + tx], k2[j]));
+        const size_t g = static_cast<size_t>(Y) * p.pitch + X;
+        p.G2[g] = acc;
+        p.D1[g] = __fsub_rn(acc, g1[(Y - ay0) * Gm::w_g1 + (X - ax0)]);
+        if (p.nextG != nullptr && ((X | Y) & 1) == 0 && (X >> 1) < p.nw && (Y >> 1) < p.nh)
+          p.nextG[static_cast<size_t>(Y >> 1) * p.npitch + (X >> 1)] = acc;
+      }
+    }
+
+    template <int K1, int K2, int TW, int TH>
+    __global__ void __launch_bounds__(HD_NT)
+        octave_head_kernel(const __grid_constant__ HeadParams p)
+    {
+      using Gm = HeadGeom<K1, K2, TW, TH>;
+      extern __shared__ float hs[];
+      const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+      const int gx0 = x0 - Gm::c2 - Gm::c1, gy0 = y0 - Gm::c2 - Gm::c1;
+      const bool inside = gx0 >= 0 && gy0 >= 0 && gx0 + Gm::w_g0 <= p.w && gy0 + Gm::h_g0 <= p.h;  // block-uniform
+      if (inside)
+        head_tile<K1, K2, TW, TH, false>(p, hs, x0, y0);
+      else
+        head_tile<K1, K2, TW, TH, true>(p, hs, x0, y0);
+    }
+
+    template <int TW, int TH>
+    bool launch_head_tiles(const HeadParams& p, cudaStream_t st)
+    {
+      using Gm = HeadGeom<11, 13, TW, TH>;
+      const int smem = Gm::smem_floats * sizeof(float);
+      if (cudaFuncSetAttribute(octave_head_kernel<11, 13, TW, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
+          cudaSuccess)
+        return false;
+      const dim3 grid((p.w + TW - 1) / TW, (p.h + TH - 1) / TH);
+      octave_head_kernel<11, 13, TW, TH><<<grid, HD_NT, smem, st>>>(p);
+      return true;
+    }
+
   }  // namespace
+
+  // Scales 1 and 2 (11 and 13 taps: the default schedule) of one octave in one launch, with D(0), D(1) and --
+  // when `next` is given -- the base of the next octave (even sampling).  False if not applicable.
+  bool launch_octave_head(const OctaveDesc& oc, const OctaveDesc* next, const Taps& t1, const Taps& t2, cudaStream_t st)
+  {
+    if (t1.n != 11 || t2.n != 13)
+      return false;
+    HeadParams p{};
+    p.G0 = oc.G;
+    p.G1 = oc.G + oc.layer_stride;
+    p.G2 = oc.G + 2 * static_cast<size_t>(oc.layer_stride);
+    p.D0 = oc.D;
+    p.D1 = oc.D + oc.layer_stride;
+    p.nextG = next ? next->G : nullptr;
+    p.w = oc.w;
+    p.h = oc.h;
+    p.pitch = oc.pitch;
+    p.nw = next ? next->w : 0;
+    p.nh = next ? next->h : 0;
+    p.npitch = next ? next->pitch : 0;
+    for (int j = 0; j < 11; ++j)
+      p.k1[j] = t1.v[j];
+    for (int j = 0; j < 13; ++j)
+      p.k2[j] = t2.v[j];
+    // 64 x 32 tiles (1.9x halo work) when they give the machine enough CTAs, 32 x 16 tiles (3.9x halo work, a
+    // quarter of the latency per CTA) for the tiny octaves
+    const int big_tiles = ((oc.w + 63) / 64) * ((oc.h + 31) / 32);
+    return big_tiles >= 100 ? launch_head_tiles<64, 32>(p, st) : launch_head_tiles<32, 16>(p, st);
+  }
 
   void launch_gaussian_stage(const float* src, int src_pitch, float* dst, int dst_pitch, float* dog,
                              int dog_pitch, int w, int h, const Taps& taps, cudaStream_t st)
