@@ -499,14 +499,14 @@ namespace sb {
     // by KC rounds of a block-wide minimum over (distance, index).
     // grid.y slices of the data range share a query; every block writes its KC best as exact
     // candidates, cand[(q * slices + slice) * KC + i], for rerank_kernel to merge.
-    __global__ void __launch_bounds__(512)
+    __global__ void __launch_bounds__(1024)
         knn_few_kernel(const float* __restrict__ queries, const int* __restrict__ qlist, const float* __restrict__ data,
                        int nd, int dim, float* __restrict__ cand_key, int* __restrict__ cand_idx)
     {
       extern __shared__ float smem[];
       float* qv = smem;  // dim floats
-      __shared__ float r_d[16];
-      __shared__ int r_i[16];
+      __shared__ float r_d[32];
+      __shared__ int r_i[32];
       const int q = qlist[blockIdx.x];
       for (int d = threadIdx.x; d < dim; d += blockDim.x)
         qv[d] = queries[static_cast<size_t>(q) * dim + d];
@@ -529,12 +529,29 @@ namespace sb {
         float result = 0.f;
         int i = 0;
         if (vec)
+        {
+          // eight 16-byte loads in flight per step; the additions keep FLANN's order
+          for (; i + 31 < dim; i += 32)
+          {
+            float4 x[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              x[u] = __ldg(reinterpret_cast<const float4*>(b + i) + u);
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+            {
+              const float d0 = x[u].x - qv[i + 4 * u], d1 = x[u].y - qv[i + 4 * u + 1];
+              const float d2 = x[u].z - qv[i + 4 * u + 2], d3 = x[u].w - qv[i + 4 * u + 3];
+              result += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+            }
+          }
           for (; i + 3 < dim; i += 4)
           {
             const float4 x = __ldg(reinterpret_cast<const float4*>(b + i));
             const float d0 = x.x - qv[i], d1 = x.y - qv[i + 1], d2 = x.z - qv[i + 2], d3 = x.w - qv[i + 3];
             result += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
           }
+        }
         else
           for (; i + 3 < dim; i += 4)
           {
@@ -935,7 +952,7 @@ namespace sb {
           if (h_redo <= 4096)
           {
             const int slices = nd >= 4096 ? MAX_SPLITS : 1;
-            knn_few_kernel<<<dim3(h_redo, slices), 512, dim * sizeof(float), st>>>(d_q, redo, d_data, nd, dim, cand_key,
+            knn_few_kernel<<<dim3(h_redo, slices), 1024, dim * sizeof(float), st>>>(d_q, redo, d_data, nd, dim, cand_key,
                                                                                   cand_idx);
             rerank_kernel<<<(h_redo * 32 + 255) / 256, 256, 0, st>>>(d_q, redo, h_redo, d_data, nd, dim, slices, k, 0, nullptr,
                                                                    nullptr, cand_key, cand_idx, d_idx, d_dist, nullptr,
