@@ -288,6 +288,13 @@ namespace sb {
           "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
           : "memory");
     }
+    // (bits(key) & mask) | tag as a single LOP3 (truth table 0xEA = (a & b) | c)
+    __device__ __forceinline__ float tag_key(float key, unsigned mask, int tag)
+    {
+      unsigned r;
+      asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(__float_as_uint(key)), "r"(mask), "r"(static_cast<unsigned>(tag)));
+      return __uint_as_float(r);
+    }
     // (m1 <= m2 <= m3) <- the three smallest of {m1, m2, m3, x}; min / max only
     __device__ __forceinline__ void insert3(float& m1, float& m2, float& m3, float x)
     {
@@ -434,6 +441,8 @@ namespace sb {
         const int row = 32 * ew + lane;  // TMEM lane
         const size_t qrow = static_cast<size_t>(blockIdx.x) * 128 + row;
         float floor3 = kBig;  // the smallest THIRD key of any chunk: everything a chunk dropped is >= it
+        unsigned tag_mask;    // ~31 in a register the optimiser cannot see through: (bits & mask) | tag is ONE lop3
+        asm volatile("mov.u32 %0, 0xffffffe0;" : "=r"(tag_mask));
         for (int i = 0; i < n_my; ++i)
         {
           const int as = i & 1;
@@ -463,7 +472,7 @@ namespace sb {
               for (int e = 0; e < 4; ++e)
               {
                 const float key = __fmaf_rn(-2.f, __uint_as_float(r[4 * g + e]), n4[e]);
-                const float x = __int_as_float((__float_as_int(key) & ~31) | (4 * g + e));
+                const float x = tag_key(key, tag_mask, 4 * g + e);
                 if (e & 1)
                   insert3(b1, b2, b3, x);
                 else
