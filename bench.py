@@ -244,6 +244,8 @@ def run_ours(args):
             nv.nvmlDeviceSetCpuAffinity(nv.nvmlDeviceGetHandleByIndex(local_rank))
         except Exception:
             pass
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner on STDOUT, where the JSON line goes
         dist.init_process_group("nccl", device_id=dev)
 
     pp = sb.ImagePyramidParams(first_octave_index=0)

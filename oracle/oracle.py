@@ -76,6 +76,10 @@ def lib() -> C.CDLL:
             C.c_float, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int,
             C.POINTER(C.c_void_p),
         ]
+        L.oracle_hessian_laplace.argtypes = [
+            fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float,
+            C.c_float, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p),
+        ]
         for name in (
             "oracle_free", "oracle_num_octaves", "oracle_num_scales",
             "oracle_num_extrema", "oracle_num_keypoints",
@@ -459,4 +463,24 @@ def compute_function_extrema(
     _check(lib().oracle_function_extrema(
         _p(img), w, h, pp[0], pp[1], pp[2], pp[3], pp[4], pp[5], pp[6], {"log": 1, "doh": 2}[which],
         extremum_thres, edge_ratio_thres, int(img_padding_sz), int(extremum_refinement_iter), C.byref(out)))
+    return SiftResult(out)
+
+
+def compute_hessian_laplace(
+    image,
+    pyramid_params: PyramidParams | None = None,
+    extremum_thres: float = 1e-5,
+    img_padding_sz: int = 1,
+    num_scales: int = 10,
+    extremum_refinement_iter: int = 5,
+) -> SiftResult:
+    """ComputeHessianLaplaceMaxima (FeatureDetectors/Hessian.hpp:84-94, Hessian.cpp:19-57): det-of-Hessian
+    maxima with Laplace scale selection (laplace_maxima, RefineExtremum.cpp:659-709)."""
+    img = _f32(image)
+    h, w = img.shape
+    pp = (pyramid_params or PyramidParams(scale_count_per_octave=4)).astuple()
+    out = C.c_void_p()
+    _check(lib().oracle_hessian_laplace(
+        _p(img), w, h, pp[0], pp[1], pp[2], pp[3], pp[4], pp[5], pp[6], extremum_thres, int(img_padding_sz),
+        int(num_scales), int(extremum_refinement_iter), C.byref(out)))
     return SiftResult(out)

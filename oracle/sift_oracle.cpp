@@ -1236,6 +1236,186 @@ namespace oracle {
       }
   }
 
+  // ------------------------------------------------------------------------ //
+  // Hessian-Laplace.
+  // FeatureDetectors/RefineExtremum.cpp:132-221 refine_extremum, 2-D version.  Returns false when the
+  // offset is too large; pos / val are only written as the reference writes them.
+  static bool refine_extremum_2d(const Image& I, int x, int y, int type, float pos[2], float& val,
+                                 int border_sz, int num_iter)
+  {
+    float g[2] = {0.f, 0.f};
+    float H[4] = {0.f, 0.f, 0.f, 0.f};
+    float h[2] = {0.f, 0.f};
+    pos[0] = static_cast<float>(x);
+    pos[1] = static_cast<float>(y);
+    for (int i = 0; i < num_iter; ++i)
+    {
+      if (x < border_sz || x >= I.w - border_sz || y < border_sz || y >= I.h - border_sz)
+        break;
+      // Differential.hpp:46-61 Gradient functor (borders replicated)
+      {
+        const float c = I(x, y);
+        g[0] = x == 0 ? (I(x + 1, y) - c) / 2 : x == I.w - 1 ? (c - I(x - 1, y)) / 2 : (I(x + 1, y) - I(x - 1, y)) / 2;
+        g[1] = y == 0 ? (I(x, y + 1) - c) / 2 : y == I.h - 1 ? (c - I(x, y - 1)) / 2 : (I(x, y + 1) - I(x, y - 1)) / 2;
+      }
+      hessian2(I, x, y, H);
+      const float det = H[0] * H[3] - H[2] * H[1];
+      const float tr = H[0] + H[3];
+      if (det <= 0.f || tr * type >= 0.f)
+      {
+        g[0] = g[1] = 0.f;
+        break;
+      }
+      // Eigen 2 x 2 inverse: adjugate times 1 / det; h = (-inverse) * g
+      const float invdet = 1.f / det;
+      const float i00 = H[3] * invdet, i01 = -H[2] * invdet, i10 = -H[1] * invdet, i11 = H[0] * invdet;
+      h[0] = (-i00) * g[0] + (-i01) * g[1];
+      h[1] = (-i10) * g[0] + (-i11) * g[1];
+      if (std::max(std::fabs(h[0]), std::fabs(h[1])) > 1.5f)
+        return false;
+      if (std::min(std::fabs(h[0]), std::fabs(h[1])) > 0.6f)
+      {
+        x += h[0] > 0 ? 1 : -1;
+        y += h[1] > 0 ? 1 : -1;
+        continue;
+      }
+      break;
+    }
+    pos[0] = static_cast<float>(x);
+    pos[1] = static_cast<float>(y);
+    const float oldval = I(x, y);
+    const float newval = oldval + 0.5f * (g[0] * h[0] + g[1] * h[1]);
+    if ((type == 1 && oldval <= newval) || (type == -1 && oldval >= newval))
+    {
+      pos[0] += h[0];
+      pos[1] += h[1];
+      val = newval;
+    }
+    return true;
+  }
+
+  // The per-layer constants of select_laplace_scale (RefineExtremum.cpp:523-657): they depend on the
+  // layer s only, never on the candidate.
+  struct LaplaceScales
+  {
+    std::vector<float> scales;      // num_scales + 1
+    std::vector<float> inc_sigma;   // blur that takes patch i - 1 to patch i; [0]: from the nearest Gaussian (<= 0: none)
+    float ratio = 0.f;
+  };
+  static LaplaceScales laplace_scales(const Pyramid& G, int s, int num_scales)
+  {
+    LaplaceScales L;
+    L.scales.resize(num_scales + 1);
+    L.inc_sigma.resize(num_scales + 1);
+    L.ratio = std::pow(2.f, 1.f / num_scales);
+    const double nearest_sigma = G.scale_relative_to_octave(s - 1);
+    L.scales[0] = static_cast<float>(G.scale_relative_to_octave(s)) / std::sqrt(2.f);
+    const double inc0 = std::sqrt(static_cast<double>(L.scales[0] * L.scales[0]) - nearest_sigma * nearest_sigma);
+    L.inc_sigma[0] = inc0 > 1e-3f ? static_cast<float>(inc0) : 0.f;  // NaN compares false: no blur
+    for (int i = 1; i <= num_scales; ++i)
+    {
+      L.scales[i] = L.ratio * L.scales[i - 1];
+      L.inc_sigma[i] = std::sqrt(L.scales[i] * L.scales[i] - L.scales[i - 1] * L.scales[i - 1]);
+    }
+    return L;
+  }
+
+  static bool select_laplace_scale(float& scale, int x, int y, int s, int o, const Pyramid& G, int num_scales,
+                                   const LaplaceScales& L)
+  {
+    const Image& nearest = G(s - 1, o);
+    const int patch_radius = static_cast<int>(std::ceil(std::sqrt(2.f) * 4.f));
+    if (x - patch_radius < 0 || x + patch_radius >= nearest.w || y - patch_radius < 0 || y + patch_radius >= nearest.h)
+      return false;
+    const int side = 2 * patch_radius + 1;
+    Image patch(side, side);
+    for (int v = 0; v < side; ++v)
+      for (int u = 0; u < side; ++u)
+        patch(u, v) = nearest(x - patch_radius + u, y - patch_radius + v);
+    std::vector<float> LoGs(num_scales + 1);
+    auto log_at_centre = [&](const Image& p, float sc) {
+      const int c = patch_radius;
+      float value = 0.f;
+      value += p(c + 1, c) + p(c - 1, c);
+      value += p(c, c + 1) + p(c, c - 1);
+      const float lap = value - 4 * p(c, c);
+      return lap * (sc * sc);
+    };
+    if (L.inc_sigma[0] > 0.f)
+      patch = gaussian(patch, L.inc_sigma[0]);
+    LoGs[0] = log_at_centre(patch, L.scales[0]);
+    for (int i = 1; i <= num_scales; ++i)
+    {
+      patch = gaussian(patch, L.inc_sigma[i]);
+      LoGs[i] = log_at_centre(patch, L.scales[i]);
+    }
+    bool is_extremum = false;
+    int i = 1;
+    for (; i < num_scales; ++i)
+    {
+      is_extremum = (LoGs[i] <= LoGs[i - 1] && LoGs[i] <= LoGs[i + 1]) || (LoGs[i] >= LoGs[i - 1] && LoGs[i] >= LoGs[i + 1]);
+      if (is_extremum)
+        break;
+    }
+    if (is_extremum)
+    {
+      const float fprime = (LoGs[i + 1] - LoGs[i - 1]) / 2.f;
+      const float fsecond = LoGs[i - 1] - 2.f * LoGs[i] + LoGs[i + 1];
+      const float hh = -fprime / fsecond;
+      scale = L.scales[i] * std::pow(L.ratio, hh);
+    }
+    return is_extremum;
+  }
+
+  // RefineExtremum.cpp:659-709 laplace_maxima.
+  static std::vector<Keypoint> laplace_maxima(const Pyramid& F, const Pyramid& G, int s, int o, float extremum_thres,
+                                              int img_padding_sz, int num_scales, int refine_iterations)
+  {
+    std::vector<Keypoint> corners;
+    const Image& I = F(s, o);
+    const LaplaceScales L = laplace_scales(G, s, num_scales);
+    for (int y = img_padding_sz; y < I.h - img_padding_sz; ++y)
+      for (int x = img_padding_sz; x < I.w - img_padding_sz; ++x)
+      {
+        if (!compare_with_neighborhood3<std::greater_equal<float>>(I(x, y), x, y, I, false))
+          continue;
+        if (I(x, y) < extremum_thres)
+          continue;
+        float scale = static_cast<float>(F.scale_relative_to_octave(s));
+        if (!select_laplace_scale(scale, x, y, s, o, G, num_scales, L))
+          continue;
+        float val = I(x, y);
+        float p[2];
+        refine_extremum_2d(I, x, y, 1, p, val, img_padding_sz, refine_iterations);
+        Keypoint c = make_oeregion(p[0], p[1], scale);
+        c.orientation = 0.f;
+        c.extremum_type = 1;
+        c.extremum_value = val;
+        c.s = s;
+        c.o = o;
+        c.xi = x;
+        c.yi = y;
+        corners.push_back(c);
+      }
+    return corners;
+  }
+
+  // FeatureDetectors/Hessian.cpp:19-57 ComputeHessianLaplaceMaxima::operator(): s = 1 .. N - 1.
+  void compute_hessian_laplace(const Image& image, const PyramidParams& pp, float extremum_thres,
+                               int img_padding_sz, int num_scales, int extremum_refinement_iter, Result& R)
+  {
+    R.G = gaussian_pyramid(image, pp, 4.f);
+    R.D = det_of_hessian_pyramid(R.G);
+    R.extrema.clear();
+    for (int o = 0; o < R.D.num_octaves; ++o)
+      for (int s = 1; s < R.D.num_scales; ++s)
+      {
+        auto e = laplace_maxima(R.D, R.G, s, o, extremum_thres, img_padding_sz, num_scales,
+                                extremum_refinement_iter);
+        R.extrema.insert(R.extrema.end(), e.begin(), e.end());
+      }
+  }
+
   // FeatureDetectors/SIFT.cpp:27-108 compute_sift_keypoints.
   void compute_sift_keypoints(const Image& image, const PyramidParams& pp,
                               float gauss_truncate, float extremum_thres,
@@ -1691,6 +1871,45 @@ int oracle_function_extrema(const float* image, int w, int h, int fo, int ns, fl
   *out = R;
   return 0;
   ORACLE_CATCH
+}
+
+// ComputeHessianLaplaceMaxima (FeatureDetectors/Hessian.hpp:84-94 defaults: ImagePyramidParams(-1, 3 + 1),
+// 1e-5, padding 1, 10 scales, 5 iterations); the det-of-Hessian pyramid is layer kind 1.
+int oracle_hessian_laplace(const float* image, int w, int h, int fo, int ns, float k,
+                           int pad, float cam, float init, int omax, float extremum_thres,
+                           int img_padding_sz, int num_scales, int refine_iter, void** out)
+{
+  ORACLE_TRY
+  auto* R = new Result;
+  try
+  {
+    compute_hessian_laplace(make_image(image, w, h), make_params(fo, ns, k, pad, cam, init, omax),
+                            extremum_thres, img_padding_sz, num_scales, refine_iter, *R);
+  }
+  catch (...)
+  {
+    delete R;
+    throw;
+  }
+  *out = R;
+  return 0;
+  ORACLE_CATCH
+}
+
+// The constants of select_laplace_scale for layer s: scales[num_scales + 1], inc_sigma[num_scales + 1]
+// (0: no blur), ratio.  Shared with the GPU library's caller so that both sides use the same bits.
+void oracle_laplace_scales(float k, float scale_initial, int s, int num_scales, float* scales, float* inc_sigma,
+                           float* ratio)
+{
+  Pyramid G;
+  G.reset(1, s + 1, scale_initial, k);
+  const LaplaceScales L = laplace_scales(G, s, num_scales);
+  for (int i = 0; i <= num_scales; ++i)
+  {
+    scales[i] = L.scales[i];
+    inc_sigma[i] = L.inc_sigma[i];
+  }
+  *ratio = L.ratio;
 }
 
 void oracle_free(void* r)

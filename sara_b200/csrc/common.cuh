@@ -112,6 +112,22 @@ namespace sb {
   // which = 1: sigma^2 Laplacian, 2: sigma^4 det Hessian; norm[s] is the scale normalisation of layer s.
   int launch_function_pyramid(const PyramidDesc& P, int which, const float* norm, cudaStream_t st);
 
+  // Per-layer constants of select_laplace_scale (RefineExtremum.cpp:523-657), made on the host: the scales of
+  // the num_scales + 1 patches and the taps of the blur that leads to each of them (n_taps 0: no blur).
+  constexpr int kLaplaceMaxScales = 16;
+  constexpr int kLaplaceMaxTaps = 65;
+  struct LaplaceTable
+  {
+    int num_scales;
+    float ratio;
+    float scales[kMaxScales][kLaplaceMaxScales + 1];
+    int n_taps[kMaxScales][kLaplaceMaxScales + 1];
+    float taps[kMaxScales][kLaplaceMaxScales + 1][kLaplaceMaxTaps];
+  };
+  int launch_laplace_maxima(const PyramidDesc& Pf, const LaplaceTable* d_table, float thres, int pad, int refine_iter,
+                            int n_segments, int* seg_offsets, Candidate* cand, int cap_cand, Keypoint* ext_tmp,
+                            int* scratch, Keypoint* ext, int cap_ext, Counters* counters, cudaStream_t st);
+
   struct ExtremaParams
   {
     float extremum_thres;

@@ -675,7 +675,259 @@ namespace sb {
       }
     }
 
+    // ---- Hessian-Laplace: laplace_maxima (FeatureDetectors/RefineExtremum.cpp:659-709) -----------
+    // pass 1: spatial local maxima of the function layers s = 1 .. N - 1 (LocalMax: v >= its eight
+    // neighbours, ImageProcessing/Extrema.hpp:50-60, 105-108) that reach the threshold.
+    __global__ void __launch_bounds__(256)
+        local_max_kernel(const __grid_constant__ PyramidDesc P, int o, float thres, int pad)
+    {
+      const OctaveDesc& oct = P.oct[o];
+      const int w = oct.w, h = oct.h, pitch = oct.pitch;
+      const int n_s = P.n_scales - 3;  // layers searched (the caller's descriptor is arranged for this)
+      const long long n = static_cast<long long>(w) * h * n_s;
+      for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+           i += static_cast<long long>(gridDim.x) * blockDim.x)
+      {
+        const int x = static_cast<int>(i % w);
+        const int y = static_cast<int>((i / w) % h);
+        const int s = static_cast<int>(i / (static_cast<long long>(w) * h)) + 1;
+        uint8_t t = 0;
+        if (pad <= x && x < w - pad && pad <= y && y < h - pad)
+        {
+          const float* Dc = oct.D + static_cast<size_t>(s) * oct.layer_stride;
+          const float v = ld(Dc, pitch, x, y);
+          bool is_max = !(v < thres);
+          for (int dy = -1; dy <= 1 && is_max; ++dy)
+            for (int dx = -1; dx <= 1; ++dx)
+              if ((dx | dy) != 0)
+                is_max = is_max && v >= ld(Dc, pitch, x + dx, y + dy);
+          if (is_max)
+          {
+            t = 1;
+            atomicAdd(oct.row_count + (s - 1) * h + y, 1);
+          }
+        }
+        oct.map[(static_cast<size_t>(s - 1) * h + y) * oct.map_pitch + x] = t;
+      }
+    }
+
+    // pass 2: a warp per candidate.  select_laplace_scale (RefineExtremum.cpp:523-657): the 13 x 13 patch of
+    // G(s - 1, o) around the candidate is blurred num_scales times (row pass, column pass, borders of the PATCH
+    // replicated: gaussian() of LinearFiltering.hpp, taps made on the host per layer), the scale-normalised
+    // Laplacian at its centre is followed along the scales, and the first local extremum of that profile
+    // fixes the scale.  Then the 2-D refine_extremum (RefineExtremum.cpp:132-221) on the function layer.
+    constexpr int LP_R = 6, LP_SIDE = 13, LP_N = LP_SIDE * LP_SIDE;
+    constexpr int LP_WARPS = 4;
+
+    __global__ void __launch_bounds__(LP_WARPS * 32)
+        laplace_refine_kernel(const __grid_constant__ PyramidDesc P, const LaplaceTable* __restrict__ T, int pad,
+                              int refine_iter, const Candidate* __restrict__ cand,
+                              const Counters* __restrict__ counters, int cap_cand, Keypoint* __restrict__ ext_tmp,
+                              int* __restrict__ keep)
+    {
+      __shared__ float s_a[LP_WARPS][LP_N + 3], s_b[LP_WARPS][LP_N + 3];
+      __shared__ float s_log[LP_WARPS][kLaplaceMaxScales + 1];
+      const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+      float* A = s_a[wid];
+      float* B = s_b[wid];
+      float* LoG = s_log[wid];
+      const int n = min(counters->n_cand, cap_cand);
+      const int ns = T->num_scales;
+      for (int i = blockIdx.x * LP_WARPS + wid; i < n; i += gridDim.x * LP_WARPS)
+      {
+        const Candidate cd = cand[i];
+        const int o = cd.so >> 8, s = cd.so & 0xff;
+        const OctaveDesc& oc = P.oct[o];
+        const int x = cd.x, y = cd.y;
+        const bool inside = x - LP_R >= 0 && x + LP_R < oc.w && y - LP_R >= 0 && y + LP_R < oc.h;  // warp-uniform
+        bool found = false;
+        float scale = 0.f;
+        if (inside)
+        {
+          const float* G = oc.G + static_cast<size_t>(s - 1) * oc.layer_stride;
+          for (int p = lane; p < LP_N; p += 32)
+          {
+            const int v = p / LP_SIDE, u = p - v * LP_SIDE;
+            A[p] = G[static_cast<size_t>(y - LP_R + v) * oc.pitch + (x - LP_R + u)];
+          }
+          __syncwarp();
+          for (int k = 0; k <= ns; ++k)
+          {
+            const int K = T->n_taps[s][k];
+            if (K > 0)
+            {
+              const float* taps = T->taps[s][k];
+              const int c = K / 2;
+              for (int p = lane; p < LP_N; p += 32)  // row pass A -> B
+              {
+                const int v = p / LP_SIDE, u = p - v * LP_SIDE;
+                float acc = 0.f;
+                for (int j = 0; j < K; ++j)
+                  acc = __fadd_rn(acc, __fmul_rn(A[v * LP_SIDE + min(max(u - c + j, 0), LP_SIDE - 1)], taps[j]));
+                B[p] = acc;
+              }
+              __syncwarp();
+              for (int p = lane; p < LP_N; p += 32)  // column pass B -> A
+              {
+                const int v = p / LP_SIDE, u = p - v * LP_SIDE;
+                float acc = 0.f;
+                for (int j = 0; j < K; ++j)
+                  acc = __fadd_rn(acc, __fmul_rn(B[min(max(v - c + j, 0), LP_SIDE - 1) * LP_SIDE + u], taps[j]));
+                A[p] = acc;
+              }
+              __syncwarp();
+            }
+            if (lane == 0)
+            {
+              const int ctr = LP_R * LP_SIDE + LP_R;
+              float value = __fadd_rn(0.f, __fadd_rn(A[ctr + 1], A[ctr - 1]));
+              value = __fadd_rn(value, __fadd_rn(A[ctr + LP_SIDE], A[ctr - LP_SIDE]));
+              const float lap = __fsub_rn(value, __fmul_rn(4.f, A[ctr]));
+              const float sc = T->scales[s][k];
+              LoG[k] = __fmul_rn(lap, __fmul_rn(sc, sc));
+            }
+            __syncwarp();
+          }
+          // first local extremum of the profile (every lane: the result is warp-uniform)
+          int k = 1;
+          for (; k < ns; ++k)
+          {
+            found = (LoG[k] <= LoG[k - 1] && LoG[k] <= LoG[k + 1]) || (LoG[k] >= LoG[k - 1] && LoG[k] >= LoG[k + 1]);
+            if (found)
+              break;
+          }
+          if (found)
+          {
+            const float fprime = __fdiv_rn(__fsub_rn(LoG[k + 1], LoG[k - 1]), 2.f);
+            const float fsecond = __fadd_rn(__fsub_rn(LoG[k - 1], __fmul_rn(2.f, LoG[k])), LoG[k + 1]);
+            const float hh = __fdiv_rn(-fprime, fsecond);
+            // std::pow(float, float): evaluated in double and rounded (agrees with a correctly rounded powf)
+            scale = __fmul_rn(T->scales[s][k], static_cast<float>(pow(static_cast<double>(T->ratio), static_cast<double>(hh))));
+          }
+          __syncwarp();
+        }
+        if (lane != 0)
+          continue;
+        keep[i] = found ? 1 : 0;
+        if (!found)
+          continue;
+        // refine_extremum, 2-D, type = 1, on the function layer
+        const float* F = oc.D + static_cast<size_t>(s) * oc.layer_stride;
+        const int pitch = oc.pitch;
+        int rx = x, ry = y;
+        float g0 = 0.f, g1 = 0.f, h0 = 0.f, h1 = 0.f;
+        float val = ld(F, pitch, x, y);
+        float px = static_cast<float>(x), py = static_cast<float>(y);
+        bool ok = true;
+#pragma unroll 1
+        for (int it = 0; it < refine_iter; ++it)
+        {
+          if (rx < pad || rx >= oc.w - pad || ry < pad || ry >= oc.h - pad)
+            break;
+          const float c = ld(F, pitch, rx, ry);
+          const float xn = ld(F, pitch, rx + 1, ry), xp = ld(F, pitch, rx - 1, ry);
+          const float yn = ld(F, pitch, rx, ry + 1), yp = ld(F, pitch, rx, ry - 1);
+          g0 = __fdiv_rn(__fsub_rn(xn, xp), 2.f);
+          g1 = __fdiv_rn(__fsub_rn(yn, yp), 2.f);
+          const float hxx = __fadd_rn(__fsub_rn(xn, __fmul_rn(2.f, c)), xp);
+          const float hyy = __fadd_rn(__fsub_rn(yn, __fmul_rn(2.f, c)), yp);
+          const float hxy = __fdiv_rn(
+              __fadd_rn(__fsub_rn(__fsub_rn(ld(F, pitch, rx + 1, ry + 1), ld(F, pitch, rx - 1, ry + 1)),
+                                  ld(F, pitch, rx + 1, ry - 1)),
+                        ld(F, pitch, rx - 1, ry - 1)),
+              4.f);
+          const float det = __fsub_rn(__fmul_rn(hxx, hyy), __fmul_rn(hxy, hxy));
+          const float tr = __fadd_rn(hxx, hyy);
+          if (det <= 0.f || tr >= 0.f)  // type == 1
+          {
+            g0 = g1 = 0.f;
+            break;
+          }
+          const float invdet = __fdiv_rn(1.f, det);
+          const float i00 = __fmul_rn(hyy, invdet), i01 = __fmul_rn(-hxy, invdet);
+          const float i10 = __fmul_rn(-hxy, invdet), i11 = __fmul_rn(hxx, invdet);
+          h0 = __fadd_rn(__fmul_rn(-i00, g0), __fmul_rn(-i01, g1));
+          h1 = __fadd_rn(__fmul_rn(-i10, g0), __fmul_rn(-i11, g1));
+          if (fmaxf(fabsf(h0), fabsf(h1)) > 1.5f)
+          {
+            ok = false;
+            break;
+          }
+          if (fminf(fabsf(h0), fabsf(h1)) > 0.6f)
+          {
+            rx += h0 > 0.f ? 1 : -1;
+            ry += h1 > 0.f ? 1 : -1;
+            continue;
+          }
+          break;
+        }
+        if (ok)
+        {
+          px = static_cast<float>(rx);
+          py = static_cast<float>(ry);
+          const float oldval = ld(F, pitch, rx, ry);
+          const float newval = __fadd_rn(oldval, __fmul_rn(0.5f, __fadd_rn(__fmul_rn(g0, h0), __fmul_rn(g1, h1))));
+          if (oldval <= newval)
+          {
+            px = __fadd_rn(px, h0);
+            py = __fadd_rn(py, h1);
+            val = newval;
+          }
+        }
+        Keypoint kp;
+        kp.x = px;
+        kp.y = py;
+        const double sc2 = static_cast<double>(scale) * static_cast<double>(scale);
+        const float a = static_cast<float>(1.0 / sc2);
+        kp.shape[0] = a;
+        kp.shape[1] = 0.f;
+        kp.shape[2] = 0.f;
+        kp.shape[3] = a;
+        kp.orientation = 0.f;
+        kp.extremum_value = val;
+        kp.type = 11;
+        kp.extremum_type = 1;
+        kp.reserved = 0;
+        kp.s = s;
+        kp.o = o;
+        kp.xi = x;
+        kp.yi = y;
+        ext_tmp[i] = kp;
+      }
+    }
+
   }  // namespace
+
+  // laplace_maxima over every octave and the layers s = 1 .. N - 1 of the function pyramid in the D stack.
+  // `Pf`: the descriptor arranged for N - 1 searched layers (n_scales = N + 2, row counters / segment bases).
+  int launch_laplace_maxima(const PyramidDesc& Pf, const LaplaceTable* d_table, float thres, int pad, int refine_iter,
+                            int n_segments, int* seg_offsets, Candidate* cand, int cap_cand, Keypoint* ext_tmp,
+                            int* scratch, Keypoint* ext, int cap_ext, Counters* counters, cudaStream_t st)
+  {
+    int launches = 0;
+    cudaMemsetAsync(Pf.oct[0].row_count, 0, sizeof(int) * n_segments, st);
+    for (int o = 0; o < Pf.n_octaves; ++o)
+    {
+      const long long n = static_cast<long long>(Pf.oct[o].w) * Pf.oct[o].h * (Pf.n_scales - 3);
+      const int blocks = static_cast<int>(std::max<long long>(1, std::min<long long>((n + 255) / 256, 148 * 16)));
+      local_max_kernel<<<blocks, 256, 0, st>>>(Pf, o, thres, pad);
+      ++launches;
+    }
+    int* chunk_off = scratch;
+    int* keep = scratch + 1024;
+    int* keep_off = keep + cap_cand;
+    launches += exclusive_scan(Pf.oct[0].row_count, seg_offsets, chunk_off, n_segments, nullptr, 0, &counters->n_cand,
+                               cap_cand, &counters->overflow, 1, st);
+    compact_rows_kernel<<<std::max(1, std::min((n_segments + 7) / 8, 148 * 16)), 256, 0, st>>>(Pf, n_segments, seg_offsets,
+                                                                                              chunk_off, cand, cap_cand);
+    laplace_refine_kernel<<<148 * 4, LP_WARPS * 32, 0, st>>>(Pf, d_table, pad, refine_iter, cand, counters, cap_cand,
+                                                             ext_tmp, keep);
+    launches += 2;
+    launches += exclusive_scan(keep, keep_off, chunk_off, 0, &counters->n_cand, cap_cand, &counters->n_ext, cap_ext,
+                               &counters->overflow, 2, st);
+    emit_kept_kernel<<<296, 256, 0, st>>>(ext_tmp, keep, keep_off, chunk_off, counters, cap_cand, ext, cap_ext);
+    return launches + 1;
+  }
 
   int launch_function_pyramid(const PyramidDesc& P, int which, const float* norm, cudaStream_t st)
   {
