@@ -243,6 +243,16 @@ SARA_B200_API int sara_b200_log_extrema(sara_b200_ctx* ctx, int slot, const floa
 SARA_B200_API int sara_b200_doh_extrema(sara_b200_ctx* ctx, int slot, const float* image, int w, int h,
                           int image_on_device, const sara_b200_dog_args* args);
 
+/* ComputeHessianLaplaceMaxima::operator() (FeatureDetectors/Hessian.hpp:60-94, Hessian.cpp:19-57):
+ * det-of-Hessian pyramid, then laplace_maxima (RefineExtremum.cpp:659-709) on s = 1 .. N - 1 -- spatial local
+ * maxima >= extremum_thres, Laplace scale selection on a 13 x 13 patch over `num_scales` (<= 16) blur steps
+ * (select_laplace_scale, RefineExtremum.cpp:523-657), 2-D refinement (RefineExtremum.cpp:132-221).  Of `args`
+ * only pyramid_params, extremum_thres, img_padding_sz and extremum_refinement_iter are used.  Reference
+ * defaults: ImagePyramidParams(-1, 3 + 1), 1e-5, padding 1, 10 scales, 5 iterations.  Results as above
+ * (sara_b200_copy_extrema; the function pyramid through sara_b200_copy_layer(which = 1)). */
+SARA_B200_API int sara_b200_hessian_laplace(sara_b200_ctx* ctx, int slot, const float* image, int w, int h,
+                              int image_on_device, const sara_b200_dog_args* args, int num_scales);
+
 /* ---- gaussian_pyramid + difference_of_gaussians_pyramid only --------------
  * (GaussianPyramid.hpp:35-125, GaussianPyramid.cpp:23-51): the "fused pyramid
  * + DoG" benchmark configuration.  Asynchronous on the slot's stream (or

@@ -108,6 +108,7 @@ struct sara_b200_ctx
   float* scratch = nullptr;       // sara_b200_gaussian / sara_b200_to_gray32f work buffers (grown on demand)
   size_t scratch_bytes = 0;
   sb::match::Workspace match_ws;  // nearest-neighbour search (match.cu)
+  sb::LaplaceTable* d_laplace = nullptr;  // constants of select_laplace_scale (Hessian-Laplace), uploaded per call
   unsigned char* match_io = nullptr;  // device copies of host descriptors + result buffers of the matcher
   size_t match_io_bytes = 0;
   char err[512] = "";
@@ -283,7 +284,7 @@ namespace {
     const int n_ext_layers = std::max(n_s - 3, 0);
     // Room for the sibling detectors (LoG / DoH: a function pyramid with as many layers as the Gaussian
     // one, searched on n_s - 2 of them): one more layer in the D stack, one more map layer.
-    const int n_fun_layers = std::max(n_s - 2, 1);
+    const int n_fun_layers = std::max(n_s - 1, 1);  // Hessian-Laplace searches s = 1 .. n_s - 1
     size_t bytes = 0;
     auto take = [&](size_t n) {
       const size_t off = bytes;
@@ -972,6 +973,7 @@ void sara_b200_destroy(sara_b200_ctx* ctx)
   cudaFree(ctx->d_gray_lut);
   cudaFree(ctx->scratch);
   cudaFree(ctx->match_io);
+  cudaFree(ctx->d_laplace);
   ctx->match_ws.release();
   delete ctx;
 }
@@ -1450,6 +1452,113 @@ int sara_b200_doh_extrema(sara_b200_ctx* ctx, int slot, const float* image, int 
                           const sara_b200_dog_args* args)
 {
   return function_extrema(ctx, slot, image, w, h, image_on_device, 2, args);
+}
+
+// ComputeHessianLaplaceMaxima::operator() (FeatureDetectors/Hessian.hpp:60-94, Hessian.cpp:19-57):
+// gaussian_pyramid, det_of_hessian_pyramid, then laplace_maxima (RefineExtremum.cpp:659-709) on the layers
+// s = 1 .. N - 1: spatial local maxima above the threshold, Laplace scale selection on a 13 x 13 patch
+// (select_laplace_scale, RefineExtremum.cpp:523-657), 2-D sub-pixel refinement.  Only extremum_thres,
+// img_padding_sz and extremum_refinement_iter of `args` are used.  Reference defaults: ImagePyramidParams(-1, 3 + 1),
+// 1e-5, padding 1, 10 scales, 5 iterations.
+int sara_b200_hessian_laplace(sara_b200_ctx* ctx, int slot, const float* image, int w, int h, int image_on_device,
+                              const sara_b200_dog_args* args, int num_scales)
+{
+  int rc = check_slot(ctx, slot);
+  if (rc)
+    return rc;
+  if (!image || !args)
+    return fail(ctx, SARA_B200_ERR_BAD_ARG, "null argument");
+  Slot& S = ctx->slots[slot];
+  if (S.busy)
+    return fail(ctx, SARA_B200_ERR_BUSY, "slot %d holds an un-collected frame", slot);
+  const sara_b200_pyramid_params& pp = args->pyramid_params;
+  if (pp.scale_count_per_octave < 2 || pp.scale_count_per_octave + 2 > kMaxScales)
+    return fail(ctx, SARA_B200_ERR_BAD_ARG, "Hessian-Laplace: scale_count_per_octave outside [2, %d]", kMaxScales - 2);
+  if (num_scales < 2 || num_scales > kLaplaceMaxScales)
+    return fail(ctx, SARA_B200_ERR_BAD_ARG, "Hessian-Laplace: num_scales outside [2, %d]", kLaplaceMaxScales);
+  if (args->img_padding_sz < 1)
+    return fail(ctx, SARA_B200_ERR_BAD_ARG, "img_padding_sz must be >= 1 (the 3 x 3 neighbourhood must stay inside the layer)");
+  DeviceGuard guard(ctx->device);
+  CU(ctx, guard.err);
+  cudaStream_t st = S.own_stream;
+  S.function_pyramid = false;
+  rc = enqueue_pyramid(ctx, S, image, w, h, image_on_device != 0, pp, 4.f, st, nullptr);
+  if (rc)
+    return rc;
+  const PyramidDesc& P = S.P;
+  float norm[kMaxScales];
+  auto scale_rel = [&](int s) {  // ImagePyramid::scale_relative_to_octave: a double
+    return std::pow(static_cast<double>(pp.scale_geometric_factor), static_cast<double>(s)) *
+           static_cast<double>(pp.scale_initial);
+  };
+  for (int s = 0; s < P.n_scales; ++s)
+  {
+    const double sr = scale_rel(s);
+    norm[s] = static_cast<float>(sr * sr * sr * sr);
+  }
+  S.total_launches += launch_function_pyramid(P, 2, norm, st);
+  S.function_pyramid = true;
+
+  // the constants of select_laplace_scale, per layer (RefineExtremum.cpp:559-603), and the blur taps
+  static thread_local LaplaceTable T;
+  std::memset(&T, 0, sizeof T);
+  T.num_scales = num_scales;
+  T.ratio = std::pow(2.f, 1.f / num_scales);
+  for (int s = 1; s < P.n_scales; ++s)
+  {
+    const double nearest_sigma = scale_rel(s - 1);
+    T.scales[s][0] = static_cast<float>(scale_rel(s)) / std::sqrt(2.f);
+    const double inc0 = std::sqrt(static_cast<double>(T.scales[s][0] * T.scales[s][0]) - nearest_sigma * nearest_sigma);
+    float inc[kLaplaceMaxScales + 1];
+    inc[0] = inc0 > 1e-3f ? static_cast<float>(inc0) : 0.f;  // NaN compares false: no blur
+    for (int i = 1; i <= num_scales; ++i)
+    {
+      T.scales[s][i] = T.ratio * T.scales[s][i - 1];
+      inc[i] = std::sqrt(T.scales[s][i] * T.scales[s][i] - T.scales[s][i - 1] * T.scales[s][i - 1]);
+    }
+    for (int i = 0; i <= num_scales; ++i)
+    {
+      if (!(inc[i] > 0.f))
+        continue;
+      Taps taps;
+      if (make_taps(inc[i], 4.f, &taps) < 0 || taps.n > kLaplaceMaxTaps)
+        return fail(ctx, SARA_B200_ERR_BAD_ARG, "Hessian-Laplace: a scale-selection blur needs more than %d taps",
+                    kLaplaceMaxTaps);
+      T.n_taps[s][i] = taps.n;
+      for (int j = 0; j < taps.n; ++j)
+        T.taps[s][i][j] = taps.v[j];
+    }
+  }
+  if (!ctx->d_laplace)
+    CU(ctx, cudaMalloc(&ctx->d_laplace, sizeof(LaplaceTable)));
+  CU(ctx, cudaMemcpyAsync(ctx->d_laplace, &T, sizeof(LaplaceTable), cudaMemcpyHostToDevice, st));
+  CU(ctx, cudaStreamSynchronize(st));  // T is reused by the next call of this thread
+
+  // descriptor arranged for N - 1 searched layers: "n_scales - 3" of the extrema kernels = N - 1
+  PyramidDesc Pf = P;
+  Pf.n_scales = P.n_scales + 2;
+  const int n_fun = P.n_scales - 1;
+  int seg_base = 0;
+  int* rows0 = P.oct[0].row_count;
+  for (int o = 0; o < P.n_octaves; ++o)
+  {
+    Pf.oct[o].row_count = rows0 + seg_base;
+    Pf.oct[o].seg_base = seg_base;
+    seg_base += n_fun * P.oct[o].h;
+  }
+  CU(ctx, cudaMemsetAsync(S.counters, 0, sizeof(Counters), st));
+  if (P.n_octaves > 0 && seg_base > 0)
+    S.total_launches += launch_laplace_maxima(Pf, ctx->d_laplace, args->extremum_thres, args->img_padding_sz,
+                                              args->extremum_refinement_iter, seg_base, S.seg_offsets, S.cand,
+                                              ctx->cap_cand, S.ext_tmp, S.scratch, S.ext, ctx->cap_ext, S.counters, st);
+  if (ctx->profiling)
+    CU(ctx, cudaEventRecord(S.ev[3], st));
+  CU(ctx, cudaGetLastError());
+  S.has_keypoints = false;
+  rc = finish_enqueue(ctx, S, st);
+  if (rc)
+    return rc;
+  return wait_slot(ctx, S);
 }
 
 int sara_b200_pyramid_enqueue(sara_b200_ctx* ctx, int slot, const float* image, int w, int h,

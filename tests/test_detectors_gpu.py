@@ -80,3 +80,53 @@ def test_function_extrema_vs_oracle(which, size, fo, ns):
     rd = O.compute_dog_extrema(img, O.PyramidParams(first_octave_index=0))
     assert len(d) == len(rd.extrema) and np.array_equal(d["xi"], rd.extrema["xi"])
     ctx.close()
+
+
+def compare_hessian_laplace(ctx, ref, n_layers):
+    for o in range(ref.num_octaves):
+        for s in range(n_layers):
+            assert ctx.dog_layer(s, o).tobytes() == ref.dog(s, o).tobytes(), (s, o)
+    e, r = ctx.extrema(), ref.extrema
+    assert len(e) == len(r)
+    for k in ("xi", "yi", "s", "o", "extremum_type"):
+        assert np.array_equal(e[k], r[k]), k
+    for k in ("x", "y", "extremum_value"):  # 2-D refinement: bit-identical
+        assert e[k].tobytes() == r[k].tobytes(), k
+    # the selected scale goes through pow(ratio, h) (libm vs CUDA): shape = scale^-2 within 1e-5 relative
+    assert np.allclose(e["shape"], r["shape"], rtol=1e-5, atol=0)
+
+
+def test_reference_hessian_laplace_smoke_kat():
+    """test_featuredetectors_hessian.cpp:23-33: default ComputeHessianLaplaceMaxima on a single bright pixel."""
+    import sara_b200 as sb
+    from oracle import oracle as O
+
+    img = np.zeros((21, 21), np.float32)
+    img[1, 1] = 1
+    det = sb.ComputeHessianLaplaceMaxima()
+    feats, _ = det(img)
+    ref = O.compute_hessian_laplace(img)
+    compare_hessian_laplace(det._ctx, ref, 4)
+
+
+@pytest.mark.parametrize("size,fo,ns,num_scales,thres", [((640, 480), 0, 4, 10, 1e-5), ((517, 389), 0, 5, 6, 1e-4),
+                                                         ((300, 200), -1, 4, 10, 1e-5)])
+def test_hessian_laplace_vs_oracle(size, fo, ns, num_scales, thres):
+    import sara_b200 as sb
+    from oracle import oracle as O
+    from sara_b200 import synthetic as S
+
+    w, h = size
+    img = S.tex(w, h, 78)
+    ctx = sb.SiftContext(w, h, device=0)
+    pp = sb.ImagePyramidParams(first_octave_index=fo, scale_count_per_octave=ns)
+    e = ctx.hessian_laplace(img, pp, thres, 2, num_scales, 5)
+    ref = O.compute_hessian_laplace(img, O.PyramidParams(first_octave_index=fo, scale_count_per_octave=ns), thres, 2,
+                                    num_scales, 5)
+    assert len(e) > 50
+    compare_hessian_laplace(ctx, ref, ns)
+    # SIFT on the same context afterwards is unaffected
+    kl = ctx.compute_sift_keypoints(img, sb.ImagePyramidParams(first_octave_index=0))
+    rk = O.compute_sift_keypoints(img, O.PyramidParams(first_octave_index=0), parallel=True)
+    assert len(kl) == len(rk.keypoints)
+    ctx.close()

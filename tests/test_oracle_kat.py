@@ -254,3 +254,21 @@ def test_doh_detector_reference_smoke():
     r = O.compute_function_extrema(img, "doh", O.PyramidParams(-1, 5, float(np.float32(2.0) ** np.float32(1.0 / 3.0)), 2),
                                    1e-6, 10.0, 1, 2)
     assert r.num_octaves >= 1 and r.num_scales == 5
+
+
+def test_hessian_laplace_reference_smoke():
+    """test_featuredetectors_hessian.cpp:23-33: default ComputeHessianLaplaceMaxima on a single bright pixel runs;
+    on a textured frame it finds maxima on every searched layer, all of them spatial maxima of their layer."""
+    img = np.zeros((21, 21), np.float32)
+    img[1, 1] = 1
+    r = O.compute_hessian_laplace(img)
+    assert r.num_scales == 4
+    from sara_b200 import synthetic as S
+
+    r = O.compute_hessian_laplace(S.tex(320, 240, 5), O.PyramidParams(first_octave_index=0, scale_count_per_octave=4))
+    e = r.extrema
+    assert len(e) > 100 and set(np.unique(e["s"]).tolist()) == {1, 2, 3}
+    for k in e[:50]:
+        D = r.dog(int(k["s"]), int(k["o"]))
+        x, y = int(k["xi"]), int(k["yi"])
+        assert D[y, x] >= D[y - 1:y + 2, x - 1:x + 2].max()
