@@ -253,6 +253,13 @@ SARA_B200_API int sara_b200_doh_extrema(sara_b200_ctx* ctx, int slot, const floa
 SARA_B200_API int sara_b200_hessian_laplace(sara_b200_ctx* ctx, int slot, const float* image, int w, int h,
                               int image_on_device, const sara_b200_dog_args* args, int num_scales);
 
+/* ComputeHarrisLaplaceCorners::operator() (FeatureDetectors/Harris.hpp:125-138, Harris.cpp:165-230): Harris
+ * cornerness of every Gaussian layer (Gradient -> second-moment matrix -> Gaussian(sigma_I) -> det - kappa
+ * trace^2, times sigma_D^2 with sigma_D = sigma_I / sqrt(2)), then laplace_maxima as above.  Reference defaults:
+ * ImagePyramidParams(-1, 2 + 1, sqrt(2), 1), kappa 0.04, 1e-6, padding 1, 10 scales, 5 iterations. */
+SARA_B200_API int sara_b200_harris_laplace(sara_b200_ctx* ctx, int slot, const float* image, int w, int h,
+                             int image_on_device, const sara_b200_dog_args* args, float kappa, int num_scales);
+
 /* ---- gaussian_pyramid + difference_of_gaussians_pyramid only --------------
  * (GaussianPyramid.hpp:35-125, GaussianPyramid.cpp:23-51): the "fused pyramid
  * + DoG" benchmark configuration.  Asynchronous on the slot's stream (or

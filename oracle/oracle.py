@@ -80,6 +80,10 @@ def lib() -> C.CDLL:
             fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float,
             C.c_float, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p),
         ]
+        L.oracle_harris_laplace.argtypes = [
+            fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float,
+            C.c_float, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p),
+        ]
         for name in (
             "oracle_free", "oracle_num_octaves", "oracle_num_scales",
             "oracle_num_extrema", "oracle_num_keypoints",
@@ -482,5 +486,25 @@ def compute_hessian_laplace(
     out = C.c_void_p()
     _check(lib().oracle_hessian_laplace(
         _p(img), w, h, pp[0], pp[1], pp[2], pp[3], pp[4], pp[5], pp[6], extremum_thres, int(img_padding_sz),
+        int(num_scales), int(extremum_refinement_iter), C.byref(out)))
+    return SiftResult(out)
+
+
+def compute_harris_laplace(
+    image,
+    pyramid_params: PyramidParams | None = None,
+    kappa: float = 0.04,
+    extremum_thres: float = 1e-6,
+    img_padding_sz: int = 1,
+    num_scales: int = 10,
+    extremum_refinement_iter: int = 5,
+) -> SiftResult:
+    """ComputeHarrisLaplaceCorners (FeatureDetectors/Harris.hpp:125-138, Harris.cpp:165-230)."""
+    img = _f32(image)
+    h, w = img.shape
+    pp = (pyramid_params or PyramidParams(-1, 3, float(np.sqrt(np.float32(2.0))), 1)).astuple()
+    out = C.c_void_p()
+    _check(lib().oracle_harris_laplace(
+        _p(img), w, h, pp[0], pp[1], pp[2], pp[3], pp[4], pp[5], pp[6], kappa, extremum_thres, int(img_padding_sz),
         int(num_scales), int(extremum_refinement_iter), C.byref(out)))
     return SiftResult(out)

@@ -1416,6 +1416,66 @@ namespace oracle {
       }
   }
 
+  // FeatureDetectors/Harris.cpp:165-230 ComputeHarrisLaplaceCorners::operator(): per layer
+  // Gradient (Differential.hpp:46-61) -> SecondMomentMatrix (g g^T, SecondMomentMatrix.hpp:31-56) ->
+  // Gaussian(sigma_I) on every coefficient -> det - kappa * pow(trace, 2) (pow(float, int) is a double
+  // expression, narrowed when stored) -> times float(sigma_D * sigma_D); then laplace_maxima, s = 1 .. N - 1.
+  Pyramid harris_cornerness_from_gaussians(const Pyramid& G, float kappa)
+  {
+    Pyramid C;
+    C.reset(G.num_octaves, G.num_scales, G.scale_initial, G.scale_geometric_factor);
+    static const float scale_factor = 1 / std::sqrt(2.f);
+    for (int o = 0; o < G.num_octaves; ++o)
+    {
+      C.oct_scaling[o] = G.oct_scaling[o];
+      for (int s = 0; s < G.num_scales; ++s)
+      {
+        const Image& g = G(s, o);
+        const float sigma_I = static_cast<float>(G.scale_relative_to_octave(s));
+        const float sigma_D = sigma_I * scale_factor;
+        Image mxx(g.w, g.h), mxy(g.w, g.h), myy(g.w, g.h);
+        for (int y = 0; y < g.h; ++y)
+          for (int x = 0; x < g.w; ++x)
+          {
+            const float c = g(x, y);
+            const float gx = x == 0 ? (g(x + 1, y) - c) / 2 : x == g.w - 1 ? (c - g(x - 1, y)) / 2 : (g(x + 1, y) - g(x - 1, y)) / 2;
+            const float gy = y == 0 ? (g(x, y + 1) - c) / 2 : y == g.h - 1 ? (c - g(x, y - 1)) / 2 : (g(x, y + 1) - g(x, y - 1)) / 2;
+            mxx(x, y) = gx * gx;
+            mxy(x, y) = gx * gy;
+            myy(x, y) = gy * gy;
+          }
+        const Image sxx = gaussian(mxx, sigma_I), sxy = gaussian(mxy, sigma_I), syy = gaussian(myy, sigma_I);
+        Image c(g.w, g.h);
+        const float norm = static_cast<float>(sigma_D * sigma_D);
+        for (size_t i = 0; i < c.data.size(); ++i)
+        {
+          const float det = sxx.data[i] * syy.data[i] - sxy.data[i] * sxy.data[i];
+          const float tr = sxx.data[i] + syy.data[i];
+          float v = static_cast<float>(det - kappa * std::pow(static_cast<double>(tr), 2));
+          v *= norm;
+          c.data[i] = v;
+        }
+        C(s, o) = std::move(c);
+      }
+    }
+    return C;
+  }
+
+  void compute_harris_laplace(const Image& image, const PyramidParams& pp, float kappa, float extremum_thres,
+                              int img_padding_sz, int num_scales, int extremum_refinement_iter, Result& R)
+  {
+    R.G = gaussian_pyramid(image, pp, 4.f);
+    R.D = harris_cornerness_from_gaussians(R.G, kappa);
+    R.extrema.clear();
+    for (int o = 0; o < R.D.num_octaves; ++o)
+      for (int s = 1; s < R.D.num_scales; ++s)
+      {
+        auto e = laplace_maxima(R.D, R.G, s, o, extremum_thres, img_padding_sz, num_scales,
+                                extremum_refinement_iter);
+        R.extrema.insert(R.extrema.end(), e.begin(), e.end());
+      }
+  }
+
   // FeatureDetectors/SIFT.cpp:27-108 compute_sift_keypoints.
   void compute_sift_keypoints(const Image& image, const PyramidParams& pp,
                               float gauss_truncate, float extremum_thres,
@@ -1910,6 +1970,29 @@ void oracle_laplace_scales(float k, float scale_initial, int s, int num_scales, 
     inc_sigma[i] = L.inc_sigma[i];
   }
   *ratio = L.ratio;
+}
+
+// ComputeHarrisLaplaceCorners (FeatureDetectors/Harris.hpp:125-138 defaults: ImagePyramidParams(-1, 2 + 1,
+// sqrt(2), 1), kappa 0.04, 1e-6, padding 1, 10 scales, 5 iterations); the cornerness pyramid is layer kind 1.
+int oracle_harris_laplace(const float* image, int w, int h, int fo, int ns, float k,
+                          int pad, float cam, float init, int omax, float kappa, float extremum_thres,
+                          int img_padding_sz, int num_scales, int refine_iter, void** out)
+{
+  ORACLE_TRY
+  auto* R = new Result;
+  try
+  {
+    compute_harris_laplace(make_image(image, w, h), make_params(fo, ns, k, pad, cam, init, omax), kappa,
+                           extremum_thres, img_padding_sz, num_scales, refine_iter, *R);
+  }
+  catch (...)
+  {
+    delete R;
+    throw;
+  }
+  *out = R;
+  return 0;
+  ORACLE_CATCH
 }
 
 void oracle_free(void* r)

@@ -12,6 +12,7 @@ from .api import (  # noqa: F401
     match,
     ComputeDoGExtrema,
     ComputeDoHExtrema,
+    ComputeHarrisLaplaceCorners,
     ComputeHessianLaplaceMaxima,
     ComputeLoGExtrema,
     ImagePyramidParams,

@@ -114,6 +114,7 @@ SYMBOLS = [
     "sara_b200_collect_device", "sara_b200_set_graphs",
     "sara_b200_default_match_args", "sara_b200_knn", "sara_b200_compute_matches",
     "sara_b200_log_extrema", "sara_b200_doh_extrema", "sara_b200_describe_extrema", "sara_b200_hessian_laplace",
+    "sara_b200_harris_laplace",
 ]
 
 
@@ -161,6 +162,8 @@ def load_library() -> C.CDLL:
     L.sara_b200_log_extrema.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.POINTER(_DogArgs)]
     L.sara_b200_doh_extrema.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.POINTER(_DogArgs)]
     L.sara_b200_hessian_laplace.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.POINTER(_DogArgs), C.c_int]
+    L.sara_b200_harris_laplace.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.POINTER(_DogArgs), C.c_float,
+                                           C.c_int]
     L.sara_b200_describe_extrema.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp, vp, C.c_int, ip]
     L.sara_b200_pyramid_enqueue.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.POINTER(_PyrParams), C.c_float, vp]
     L.sara_b200_num_octaves.argtypes = [vp, C.c_int]
@@ -501,6 +504,17 @@ class SiftContext:
         del keep
         return self.extrema(slot)
 
+    def harris_laplace(self, image, pyramid_params=None, kappa=0.04, extremum_thres=1e-6, img_padding_sz=1,
+                       num_scales=10, extremum_refinement_iter=5, slot=0) -> np.ndarray:
+        """ComputeHarrisLaplaceCorners (Harris.hpp:125-138)."""
+        ptr, w, h, on_dev, keep = _as_image(image)
+        pp = pyramid_params or ImagePyramidParams(-1, 3, float(np.sqrt(np.float32(2.0))), 1)
+        args = _DogArgs(pp._c(), 4.0, extremum_thres, 10.0, int(img_padding_sz), int(extremum_refinement_iter))
+        self._check(self._L.sara_b200_harris_laplace(self._ctx, slot, ptr, w, h, int(on_dev), C.byref(args), kappa,
+                                                     int(num_scales)))
+        del keep
+        return self.extrema(slot)
+
     def describe_extrema(self, extrema, slot=0):
         """ComputeDominantOrientations + ComputeSIFTDescriptor<4, 8> (+ rescale) on the given extrema against the
         pyramid the slot holds.  Returns (oriented keypoints in octave coordinates, KeypointList in image
@@ -691,6 +705,32 @@ class ComputeHessianLaplaceMaxima:
         return self._ctx.gaussian_layer(s, o)
 
     def det_of_hessians(self, s, o):
+        return self._ctx.dog_layer(s, o)
+
+
+class ComputeHarrisLaplaceCorners:
+    """DO::Sara::ComputeHarrisLaplaceCorners (FeatureDetectors/Harris.hpp:95-175): constructor defaults
+    ImagePyramidParams(-1, 2 + 1, sqrt(2), 1), kappa 0.04, 1e-6, 1, 10 scales, 5 iterations; call operator;
+    gaussians / harris."""
+
+    def __init__(self, pyramid_params: ImagePyramidParams | None = None, kappa=0.04, extremum_thres=1e-6,
+                 img_padding_sz=1, scale_count=10, extremum_refinement_iter=5, device: int = 0):
+        self.params = pyramid_params or ImagePyramidParams(-1, 3, float(np.sqrt(np.float32(2.0))), 1)
+        self.args = (kappa, extremum_thres, img_padding_sz, scale_count, extremum_refinement_iter)
+        self.device = device
+        self._ctx = None
+
+    def __call__(self, image):
+        _, w, h, _, _ = _as_image(image)
+        if self._ctx is None:
+            self._ctx = SiftContext(w, h, self.device, min_first_octave_index=min(self.params.first_octave_index, 0))
+        e = self._ctx.harris_laplace(image, self.params, *self.args)
+        return e, np.stack([e["s"], e["o"]], axis=1)
+
+    def gaussians(self, s, o):
+        return self._ctx.gaussian_layer(s, o)
+
+    def harris(self, s, o):
         return self._ctx.dog_layer(s, o)
 
 

@@ -128,6 +128,12 @@ namespace sb {
                             int n_segments, int* seg_offsets, Candidate* cand, int cap_cand, Keypoint* ext_tmp,
                             int* scratch, Keypoint* ext, int cap_ext, Counters* counters, cudaStream_t st);
 
+  // Harris cornerness (extrema.cu): g g^T of the Gradient functor, and det - kappa trace^2 (in double, as
+  // pow(float, int) makes it in the reference) times the scale normalisation.
+  void launch_second_moment(const float* G, int w, int h, int pitch, float* mxx, float* mxy, float* myy, cudaStream_t st);
+  void launch_cornerness(const float* sxx, const float* sxy, const float* syy, int w, int h, int pitch, float kappa,
+                         float norm, float* dst, cudaStream_t st);
+
   struct ExtremaParams
   {
     float extremum_thres;

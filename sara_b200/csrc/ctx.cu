@@ -1460,8 +1460,8 @@ int sara_b200_doh_extrema(sara_b200_ctx* ctx, int slot, const float* image, int 
 // (select_laplace_scale, RefineExtremum.cpp:523-657), 2-D sub-pixel refinement.  Only extremum_thres,
 // img_padding_sz and extremum_refinement_iter of `args` are used.  Reference defaults: ImagePyramidParams(-1, 3 + 1),
 // 1e-5, padding 1, 10 scales, 5 iterations.
-int sara_b200_hessian_laplace(sara_b200_ctx* ctx, int slot, const float* image, int w, int h, int image_on_device,
-                              const sara_b200_dog_args* args, int num_scales)
+static int laplace_detector(sara_b200_ctx* ctx, int slot, const float* image, int w, int h, int image_on_device,
+                            const sara_b200_dog_args* args, int num_scales, bool harris, float kappa)
 {
   int rc = check_slot(ctx, slot);
   if (rc)
@@ -1473,7 +1473,7 @@ int sara_b200_hessian_laplace(sara_b200_ctx* ctx, int slot, const float* image, 
     return fail(ctx, SARA_B200_ERR_BUSY, "slot %d holds an un-collected frame", slot);
   const sara_b200_pyramid_params& pp = args->pyramid_params;
   if (pp.scale_count_per_octave < 2 || pp.scale_count_per_octave + 2 > kMaxScales)
-    return fail(ctx, SARA_B200_ERR_BAD_ARG, "Hessian-Laplace: scale_count_per_octave outside [2, %d]", kMaxScales - 2);
+    return fail(ctx, SARA_B200_ERR_BAD_ARG, "Laplace detectors: scale_count_per_octave outside [2, %d]", kMaxScales - 2);
   if (num_scales < 2 || num_scales > kLaplaceMaxScales)
     return fail(ctx, SARA_B200_ERR_BAD_ARG, "Hessian-Laplace: num_scales outside [2, %d]", kLaplaceMaxScales);
   if (args->img_padding_sz < 1)
@@ -1491,12 +1491,47 @@ int sara_b200_hessian_laplace(sara_b200_ctx* ctx, int slot, const float* image, 
     return std::pow(static_cast<double>(pp.scale_geometric_factor), static_cast<double>(s)) *
            static_cast<double>(pp.scale_initial);
   };
-  for (int s = 0; s < P.n_scales; ++s)
+  if (!harris)
   {
-    const double sr = scale_rel(s);
-    norm[s] = static_cast<float>(sr * sr * sr * sr);
+    for (int s = 0; s < P.n_scales; ++s)
+    {
+      const double sr = scale_rel(s);
+      norm[s] = static_cast<float>(sr * sr * sr * sr);
+    }
+    S.total_launches += launch_function_pyramid(P, 2, norm, st);
   }
-  S.total_launches += launch_function_pyramid(P, 2, norm, st);
+  else
+  {
+    // ComputeHarrisLaplaceCorners (Harris.cpp:171-193): per layer Gradient -> SecondMomentMatrix ->
+    // Gaussian(sigma_I) of every coefficient -> det - kappa trace^2 -> times float(sigma_D^2)
+    const float scale_factor = 1 / std::sqrt(2.f);
+    const size_t layer0 = align_up(sizeof(float) * P.oct[0].pitch * P.oct[0].h, 256);
+    rc = grow_scratch(ctx, 6 * layer0);
+    if (rc)
+      return rc;
+    for (int o = 0; o < P.n_octaves; ++o)
+    {
+      const OctaveDesc& oc = P.oct[o];
+      const size_t layer = static_cast<size_t>(oc.pitch) * oc.h;
+      float* m[6];
+      for (int c = 0; c < 6; ++c)
+        m[c] = ctx->scratch + c * (layer0 / sizeof(float));
+      for (int s = 0; s < P.n_scales; ++s)
+      {
+        const float sigma_I = static_cast<float>(scale_rel(s));
+        const float sigma_D = sigma_I * scale_factor;
+        Taps taps;
+        if (make_taps(sigma_I, 4.f, &taps) < 0)
+          return fail(ctx, SARA_B200_ERR_BAD_ARG, "Harris-Laplace: the integration blur exceeds %d taps", kMaxTaps);
+        launch_second_moment(oc.G + s * layer, oc.w, oc.h, oc.pitch, m[0], m[1], m[2], st);
+        for (int c = 0; c < 3; ++c)
+          launch_gaussian_stage(m[c], oc.pitch, m[3 + c], oc.pitch, nullptr, 0, oc.w, oc.h, taps, st);
+        launch_cornerness(m[3], m[4], m[5], oc.w, oc.h, oc.pitch, kappa, static_cast<float>(sigma_D * sigma_D),
+                          oc.D + s * layer, st);
+        S.total_launches += 5;
+      }
+    }
+  }
   S.function_pyramid = true;
 
   // the constants of select_laplace_scale, per layer (RefineExtremum.cpp:559-603), and the blur taps
@@ -1559,6 +1594,22 @@ int sara_b200_hessian_laplace(sara_b200_ctx* ctx, int slot, const float* image, 
   if (rc)
     return rc;
   return wait_slot(ctx, S);
+}
+
+int sara_b200_hessian_laplace(sara_b200_ctx* ctx, int slot, const float* image, int w, int h, int image_on_device,
+                              const sara_b200_dog_args* args, int num_scales)
+{
+  return laplace_detector(ctx, slot, image, w, h, image_on_device, args, num_scales, false, 0.f);
+}
+
+// ComputeHarrisLaplaceCorners::operator() (FeatureDetectors/Harris.hpp:125-138, Harris.cpp:165-230): the Harris
+// cornerness of every Gaussian layer (integration scale sigma_I = the layer's scale, differentiation scale
+// sigma_I / sqrt(2)), then laplace_maxima on s = 1 .. N - 1.  Reference defaults: ImagePyramidParams(-1, 2 + 1,
+// sqrt(2), 1), kappa 0.04, 1e-6, padding 1, 10 scales, 5 iterations.
+int sara_b200_harris_laplace(sara_b200_ctx* ctx, int slot, const float* image, int w, int h, int image_on_device,
+                             const sara_b200_dog_args* args, float kappa, int num_scales)
+{
+  return laplace_detector(ctx, slot, image, w, h, image_on_device, args, num_scales, true, kappa);
 }
 
 int sara_b200_pyramid_enqueue(sara_b200_ctx* ctx, int slot, const float* image, int w, int h,

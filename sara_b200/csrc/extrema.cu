@@ -896,7 +896,67 @@ namespace sb {
       }
     }
 
+    // ---- Harris cornerness (FeatureDetectors/Harris.cpp:171-193) -----------------------------------
+    __global__ void __launch_bounds__(256)
+        second_moment_kernel(const float* __restrict__ G, int w, int h, int pitch, float* __restrict__ mxx,
+                             float* __restrict__ mxy, float* __restrict__ myy)
+    {
+      const long long n = static_cast<long long>(w) * h;
+      for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+           i += static_cast<long long>(gridDim.x) * blockDim.x)
+      {
+        const int x = static_cast<int>(i % w), y = static_cast<int>(i / w);
+        const float c = ld(G, pitch, x, y);
+        // Gradient functor, Differential.hpp:46-61 (one-sided differences on the border, all divided by 2)
+        const float gx = x == 0       ? __fdiv_rn(__fsub_rn(ld(G, pitch, x + 1, y), c), 2.f)
+                         : x == w - 1 ? __fdiv_rn(__fsub_rn(c, ld(G, pitch, x - 1, y)), 2.f)
+                                      : __fdiv_rn(__fsub_rn(ld(G, pitch, x + 1, y), ld(G, pitch, x - 1, y)), 2.f);
+        const float gy = y == 0       ? __fdiv_rn(__fsub_rn(ld(G, pitch, x, y + 1), c), 2.f)
+                         : y == h - 1 ? __fdiv_rn(__fsub_rn(c, ld(G, pitch, x, y - 1)), 2.f)
+                                      : __fdiv_rn(__fsub_rn(ld(G, pitch, x, y + 1), ld(G, pitch, x, y - 1)), 2.f);
+        const size_t g = static_cast<size_t>(y) * pitch + x;
+        mxx[g] = __fmul_rn(gx, gx);
+        mxy[g] = __fmul_rn(gx, gy);
+        myy[g] = __fmul_rn(gy, gy);
+      }
+    }
+
+    __global__ void __launch_bounds__(256)
+        cornerness_kernel(const float* __restrict__ sxx, const float* __restrict__ sxy, const float* __restrict__ syy,
+                          int w, int h, int pitch, float kappa, float norm, float* __restrict__ dst)
+    {
+      const long long n = static_cast<long long>(w) * h;
+      for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+           i += static_cast<long long>(gridDim.x) * blockDim.x)
+      {
+        const int x = static_cast<int>(i % w), y = static_cast<int>(i / w);
+        const size_t g = static_cast<size_t>(y) * pitch + x;
+        const float a = sxx[g], b = sxy[g], d = syy[g];
+        const float det = __fsub_rn(__fmul_rn(a, d), __fmul_rn(b, b));
+        const float tr = __fadd_rn(a, d);
+        // det - kappa * pow(trace, 2): pow(float, int) is a double, so the whole expression is (Harris.cpp:185-188)
+        const double t2 = static_cast<double>(tr) * static_cast<double>(tr);
+        const float v = static_cast<float>(__dsub_rn(static_cast<double>(det), __dmul_rn(static_cast<double>(kappa), t2)));
+        dst[g] = __fmul_rn(v, norm);
+      }
+    }
+
   }  // namespace
+
+  void launch_second_moment(const float* G, int w, int h, int pitch, float* mxx, float* mxy, float* myy, cudaStream_t st)
+  {
+    const long long n = static_cast<long long>(w) * h;
+    const int blocks = static_cast<int>(std::max<long long>(1, std::min<long long>((n + 255) / 256, 148 * 16)));
+    second_moment_kernel<<<blocks, 256, 0, st>>>(G, w, h, pitch, mxx, mxy, myy);
+  }
+
+  void launch_cornerness(const float* sxx, const float* sxy, const float* syy, int w, int h, int pitch, float kappa,
+                         float norm, float* dst, cudaStream_t st)
+  {
+    const long long n = static_cast<long long>(w) * h;
+    const int blocks = static_cast<int>(std::max<long long>(1, std::min<long long>((n + 255) / 256, 148 * 16)));
+    cornerness_kernel<<<blocks, 256, 0, st>>>(sxx, sxy, syy, w, h, pitch, kappa, norm, dst);
+  }
 
   // laplace_maxima over every octave and the layers s = 1 .. N - 1 of the function pyramid in the D stack.
   // `Pf`: the descriptor arranged for N - 1 searched layers (n_scales = N + 2, row counters / segment bases).

@@ -130,3 +130,33 @@ def test_hessian_laplace_vs_oracle(size, fo, ns, num_scales, thres):
     rk = O.compute_sift_keypoints(img, O.PyramidParams(first_octave_index=0), parallel=True)
     assert len(kl) == len(rk.keypoints)
     ctx.close()
+
+
+def test_reference_harris_laplace_smoke_kat():
+    """test_featuredetectors_harris.cpp:35-45: default ComputeHarrisLaplaceCorners on a single bright pixel."""
+    import sara_b200 as sb
+    from oracle import oracle as O
+
+    img = np.zeros((21, 21), np.float32)
+    img[1, 1] = 1
+    det = sb.ComputeHarrisLaplaceCorners()
+    det(img)
+    compare_hessian_laplace(det._ctx, O.compute_harris_laplace(img), 3)
+
+
+@pytest.mark.parametrize("size,fo,ns,k,thres", [((640, 480), 0, 3, None, 1e-9), ((517, 389), 0, 4, 2.0 ** (1 / 3), 1e-8),
+                                                ((300, 200), -1, 3, None, 1e-9)])
+def test_harris_laplace_vs_oracle(size, fo, ns, k, thres):
+    import sara_b200 as sb
+    from oracle import oracle as O
+    from sara_b200 import synthetic as S
+
+    w, h = size
+    img = S.tex(w, h, 79)
+    kk = float(np.sqrt(np.float32(2.0))) if k is None else float(np.float32(k))
+    ctx = sb.SiftContext(w, h, device=0)
+    e = ctx.harris_laplace(img, sb.ImagePyramidParams(fo, ns, kk, 1), 0.04, thres, 2, 10, 5)
+    ref = O.compute_harris_laplace(img, O.PyramidParams(fo, ns, kk, 1), 0.04, thres, 2, 10, 5)
+    assert len(e) > 50
+    compare_hessian_laplace(ctx, ref, ns)
+    ctx.close()
