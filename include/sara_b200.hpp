@@ -301,6 +301,184 @@ namespace sara_b200 {
                            [](int n, int d) { return DescriptorMatrix{n, d}; });
   }
 
+  // ---- detector functors: ComputeDoGExtrema (FeatureDetectors/DoG.hpp:72-165), ComputeLoGExtrema
+  // (LoG.hpp:71-117), ComputeDoHExtrema / ComputeHessianLaplaceMaxima (Hessian.hpp:60-240),
+  // ComputeHarrisLaplaceCorners (Harris.hpp:95-175): same constructor arguments and defaults, same call
+  // operator `std::vector<OERegion> operator()(const ImageView<float>&, std::vector<Point2i>* scale_octave_pairs)`.
+  struct Point2i
+  {
+    int v[2] = {0, 0};
+    int operator()(int i) const { return v[i]; }
+    int& operator()(int i) { return v[i]; }
+  };
+
+  namespace detail {
+    template <typename Call>
+    inline std::vector<OERegion> run_detector(const ImageView<float>& I, std::vector<Point2i>* scale_octave_pairs,
+                                              Call&& call)
+    {
+      Context& ctx = default_context(I.width(), I.height());
+      int rc = call(ctx.get());
+      if (rc != 0)
+        rethrow(rc, ctx.get());
+      int n = 0;
+      rc = sara_b200_copy_extrema(ctx.get(), 0, nullptr, 0, &n);
+      std::vector<sara_b200_keypoint> raw(static_cast<std::size_t>(n > 0 ? n : 1));
+      if (n > 0)
+      {
+        rc = sara_b200_copy_extrema(ctx.get(), 0, raw.data(), n, &n);
+        if (rc != 0)
+          rethrow(rc, ctx.get());
+      }
+      std::vector<OERegion> out(static_cast<std::size_t>(n));
+      if (scale_octave_pairs)
+        scale_octave_pairs->assign(static_cast<std::size_t>(n), Point2i{});
+      for (int i = 0; i < n; ++i)
+      {
+        const sara_b200_keypoint& k = raw[i];
+        OERegion& r = out[i];
+        r.coords(0) = k.x;
+        r.coords(1) = k.y;
+        r.shape_matrix(0, 0) = k.shape[0];
+        r.shape_matrix(1, 0) = k.shape[1];
+        r.shape_matrix(0, 1) = k.shape[2];
+        r.shape_matrix(1, 1) = k.shape[3];
+        r.orientation = k.orientation;
+        r.extremum_value = k.extremum_value;
+        r.type = static_cast<OERegion::Type>(k.type);
+        r.extremum_type = static_cast<OERegion::ExtremumType>(k.extremum_type);
+        if (scale_octave_pairs)
+        {
+          (*scale_octave_pairs)[i](0) = k.s;
+          (*scale_octave_pairs)[i](1) = k.o;
+        }
+      }
+      return out;
+    }
+
+    inline sara_b200_dog_args dog_args(const ImagePyramidParams& pp, float gauss_truncate, float thres, float edge_ratio,
+                                       int padding, int iters)
+    {
+      sara_b200_dog_args a;
+      a.pyramid_params = pp.c_params();
+      a.gauss_truncate = gauss_truncate;
+      a.extremum_thres = thres;
+      a.edge_ratio_thres = edge_ratio;
+      a.img_padding_sz = padding;
+      a.extremum_refinement_iter = iters;
+      return a;
+    }
+  }  // namespace detail
+
+  class ComputeDoGExtrema
+  {
+  public:
+    ComputeDoGExtrema(const ImagePyramidParams& pyramid_params = ImagePyramidParams(), float gauss_truncate = 4.f,
+                      float extremum_thres = 0.01f, float edge_ratio_thres = 10.f, int img_padding_sz = 1,
+                      int extremum_refinement_iter = 5)
+      : _args{detail::dog_args(pyramid_params, gauss_truncate, extremum_thres, edge_ratio_thres, img_padding_sz,
+                               extremum_refinement_iter)}
+    {
+      if (pyramid_params.scale_count_per_octave() < 4)  // DoG.hpp:86-89
+        throw std::runtime_error{"Error: The extraction of DoG extrema needs (1 + 3) = 4 scales per octave at the very "
+                                 "minimum!"};
+    }
+    std::vector<OERegion> operator()(const ImageView<float>& I, std::vector<Point2i>* scale_octave_pairs = nullptr)
+    {
+      return detail::run_detector(I, scale_octave_pairs, [&](sara_b200_ctx* c) {
+        return sara_b200_dog_extrema(c, 0, I.data(), I.width(), I.height(), 0, &_args);
+      });
+    }
+
+  private:
+    sara_b200_dog_args _args;
+  };
+
+  class ComputeLoGExtrema
+  {
+  public:
+    ComputeLoGExtrema(const ImagePyramidParams& pyr_params = ImagePyramidParams(-1, 3 + 2), float extremum_thres = 0.01f,
+                      float edge_ratio_thres = 10.f, int img_padding_sz = 1, int extremum_refinement_iter = 5)
+      : _args{detail::dog_args(pyr_params, 4.f, extremum_thres, edge_ratio_thres, img_padding_sz, extremum_refinement_iter)}
+    {
+    }
+    std::vector<OERegion> operator()(const ImageView<float>& I, std::vector<Point2i>* scale_octave_pairs = nullptr)
+    {
+      return detail::run_detector(I, scale_octave_pairs, [&](sara_b200_ctx* c) {
+        return sara_b200_log_extrema(c, 0, I.data(), I.width(), I.height(), 0, &_args);
+      });
+    }
+
+  private:
+    sara_b200_dog_args _args;
+  };
+
+  class ComputeDoHExtrema
+  {
+  public:
+    ComputeDoHExtrema(const ImagePyramidParams& pyr_params = ImagePyramidParams(-1, 3 + 2, std::pow(2.f, 1.f / 3.f), 2),
+                      float extremum_thres = 1e-6f, float edge_ratio_thres = 10.f, int img_padding_sz = 1,
+                      int extremum_refinement_iter = 2)
+      : _args{detail::dog_args(pyr_params, 4.f, extremum_thres, edge_ratio_thres, img_padding_sz, extremum_refinement_iter)}
+    {
+    }
+    std::vector<OERegion> operator()(const ImageView<float>& I, std::vector<Point2i>* scale_octave_pairs = nullptr)
+    {
+      return detail::run_detector(I, scale_octave_pairs, [&](sara_b200_ctx* c) {
+        return sara_b200_doh_extrema(c, 0, I.data(), I.width(), I.height(), 0, &_args);
+      });
+    }
+
+  private:
+    sara_b200_dog_args _args;
+  };
+
+  class ComputeHessianLaplaceMaxima
+  {
+  public:
+    ComputeHessianLaplaceMaxima(const ImagePyramidParams& pyr_params = ImagePyramidParams(-1, 3 + 1),
+                                float extremum_thres = 1e-5f, int img_padding_sz = 1, int num_scales = 10,
+                                int extremum_refinement_iter = 5)
+      : _args{detail::dog_args(pyr_params, 4.f, extremum_thres, 10.f, img_padding_sz, extremum_refinement_iter)}
+      , _num_scales{num_scales}
+    {
+    }
+    std::vector<OERegion> operator()(const ImageView<float>& I, std::vector<Point2i>* scale_octave_pairs = nullptr)
+    {
+      return detail::run_detector(I, scale_octave_pairs, [&](sara_b200_ctx* c) {
+        return sara_b200_hessian_laplace(c, 0, I.data(), I.width(), I.height(), 0, &_args, _num_scales);
+      });
+    }
+
+  private:
+    sara_b200_dog_args _args;
+    int _num_scales;
+  };
+
+  class ComputeHarrisLaplaceCorners
+  {
+  public:
+    ComputeHarrisLaplaceCorners(const ImagePyramidParams& pyr_params = ImagePyramidParams(-1, 2 + 1, std::sqrt(2.f), 1),
+                                float kappa = 0.04f, float extremum_thres = 1e-6f, int img_padding_sz = 1,
+                                int scale_count = 10, int extremum_refinement_iter = 5)
+      : _args{detail::dog_args(pyr_params, 4.f, extremum_thres, 10.f, img_padding_sz, extremum_refinement_iter)}
+      , _kappa{kappa}
+      , _scale_count{scale_count}
+    {
+    }
+    std::vector<OERegion> operator()(const ImageView<float>& I, std::vector<Point2i>* scale_octave_pairs = nullptr)
+    {
+      return detail::run_detector(I, scale_octave_pairs, [&](sara_b200_ctx* c) {
+        return sara_b200_harris_laplace(c, 0, I.data(), I.width(), I.height(), 0, &_args, _kappa, _scale_count);
+      });
+    }
+
+  private:
+    sara_b200_dog_args _args;
+    float _kappa;
+    int _scale_count;
+  };
+
   // ---- Match + AnnMatcher (Match/Match.hpp:27-177, FeatureMatching/AnnMatcher.hpp:33-84) ---- //
   class Match
   {

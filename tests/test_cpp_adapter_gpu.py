@@ -181,3 +181,87 @@ def test_cpp_ann_matcher(tmp_path):
     assert np.array_equal(rec["x"], ref["x_index"]) and np.array_equal(rec["y"], ref["y_index"])
     assert np.array_equal(rec["rank"], ref["rank"])
     assert np.array_equal(rec["score"].view(np.uint32), ref["score"].view(np.uint32))
+
+
+DETECTOR_PROGRAM = r"""
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "sara_b200.hpp"
+
+namespace sara = sara_b200;
+
+int main(int argc, char** argv)
+{
+  const int w = std::atoi(argv[2]), h = std::atoi(argv[3]);
+  std::vector<float> img(static_cast<std::size_t>(w) * h);
+  FILE* f = std::fopen(argv[1], "rb");
+  if (!f || std::fread(img.data(), sizeof(float), img.size(), f) != img.size())
+    return 2;
+  std::fclose(f);
+  const sara::ImageView<float> I{img.data(), w, h};
+  std::vector<sara::Point2i> so;
+  f = std::fopen(argv[4], "wb");
+  auto dump = [&](const std::vector<sara::OERegion>& e) {
+    const int n = static_cast<int>(e.size());
+    std::fwrite(&n, sizeof(int), 1, f);
+    for (int i = 0; i < n; ++i)
+    {
+      const float rec[5] = {e[i].x(), e[i].y(), e[i].shape_matrix(0, 0), float(so[i](0)), float(so[i](1))};
+      std::fwrite(rec, sizeof(float), 5, f);
+    }
+  };
+  // the reference's own test setups: test_featuredetectors_{dog,log,hessian,harris}.cpp construct the functors
+  // with their default arguments (first octave 0 here to keep the frame small)
+  dump(sara::ComputeDoGExtrema{sara::ImagePyramidParams(0)}(I, &so));
+  dump(sara::ComputeLoGExtrema{sara::ImagePyramidParams(0, 3 + 2)}(I, &so));
+  dump(sara::ComputeDoHExtrema{sara::ImagePyramidParams(0, 3 + 2, std::pow(2.f, 1.f / 3.f), 2)}(I, &so));
+  dump(sara::ComputeHessianLaplaceMaxima{sara::ImagePyramidParams(0, 3 + 1)}(I, &so));
+  dump(sara::ComputeHarrisLaplaceCorners{sara::ImagePyramidParams(0, 2 + 1, std::sqrt(2.f), 1), 0.04f, 1e-9f}(I, &so));
+  std::fclose(f);
+  try
+  {
+    sara::ComputeDoGExtrema{sara::ImagePyramidParams(0, 3)};
+    return 3;
+  }
+  catch (const std::runtime_error&)
+  {
+  }
+  return 0;
+}
+"""
+
+
+def test_cpp_detector_functors(tmp_path):
+    w, h = 480, 360
+    img = S.tex(w, h, 321)
+    raw = tmp_path / "img.f32"
+    img.tofile(raw)
+    src = tmp_path / "det.cpp"
+    src.write_text(DETECTOR_PROGRAM)
+    exe = tmp_path / "det"
+    lib = sb.library_path()
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), lib,
+                           f"-Wl,-rpath,{os.path.dirname(lib)}"])
+    out = tmp_path / "out.bin"
+    assert subprocess.call([str(exe), str(raw), str(w), str(h), str(out)]) == 0
+    blob = np.fromfile(out, dtype=np.uint8)
+    ctx = sb.SiftContext(w, h, device=0)
+    k3 = float(np.float32(2.0) ** np.float32(1.0 / 3.0))
+    expected = [
+        ctx.dog_extrema(img, sb.ImagePyramidParams(0)),
+        ctx.function_extrema("log", img, sb.ImagePyramidParams(0, 5)),
+        ctx.function_extrema("doh", img, sb.ImagePyramidParams(0, 5, k3, 2), 1e-6, 10.0, 1, 2),
+        ctx.hessian_laplace(img, sb.ImagePyramidParams(0, 4)),
+        ctx.harris_laplace(img, sb.ImagePyramidParams(0, 3, float(np.sqrt(np.float32(2.0))), 1), 0.04, 1e-9),
+    ]
+    off = 0
+    for e in expected:
+        n = int(blob[off:off + 4].view(np.int32)[0])
+        rec = blob[off + 4:off + 4 + 20 * n].view(np.float32).reshape(n, 5)
+        off += 4 + 20 * n
+        assert n == len(e) and n > 0
+        assert np.array_equal(rec[:, 0], e["x"]) and np.array_equal(rec[:, 1], e["y"])
+        assert np.array_equal(rec[:, 2], e["shape"][:, 0])
+        assert np.array_equal(rec[:, 3], e["s"].astype(np.float32)) and np.array_equal(rec[:, 4], e["o"].astype(np.float32))
+    ctx.close()
