@@ -6,7 +6,7 @@
 
 A "step" is one pass of the whole SIFT chain (Gaussian pyramid -> DoG -> extrema ->
 orientation -> descriptor) over one batch of FRAMES_PER_STEP (16) distinct synthetic
-3840x2160 frames per GPU (first octave 0, default SIFT arguments, all 10 octaves), SLOTS (4)
+3840x2160 frames per GPU (first octave 0, default SIFT arguments, all 10 octaves), SLOTS (8)
 frames in flight.
 
  * value   : keypoints/s with the frames already resident in HBM (device pointers passed
@@ -43,7 +43,7 @@ sys.path.insert(0, ROOT)
 
 W4K, H4K = 3840, 2160  # the metric's configuration; --frame 1920x1080 measures config C4 instead
 FRAMES_PER_STEP = int(os.environ.get("SARA_B200_BENCH_FRAMES", "16"))
-SLOTS = int(os.environ.get("SARA_B200_BENCH_SLOTS", "4"))
+SLOTS = int(os.environ.get("SARA_B200_BENCH_SLOTS", "8"))
 METRIC = "sift_keypoints_per_sec_4k"
 UNIT = "keypoints/s"
 ALGO_BYTES_PER_OCTAVE_PIXEL = 48  # 1 fp32 read + 6 Gaussian + 5 DoG fp32 writes
