@@ -70,6 +70,9 @@ namespace sb {
 
         const int side = 2 * radius + 1;
         const int count = side * side;
+        const unsigned magic = (1u << 22) / static_cast<unsigned>(side) + 1u;
+        // windows that (with the gradient stencil) lie inside the layer skip the border variants of the loads
+        const bool interior = rx - radius >= 1 && rx + radius <= w - 2 && ry - radius >= 1 && ry + radius <= h - 2;
         // three samples per lane and round, their gradient loads requested together
         for (int t0 = lane; t0 < count; t0 += 96)
         {
@@ -80,13 +83,22 @@ namespace sb {
           for (int k = 0; k < 3; ++k)
           {
             const int t = t0 + 32 * k;
-            const int vr = t / side;
+            // t / side by a magic multiply (exact while side^3 < 2^22: radius < 80)
+            const int vr = side < 160 ? static_cast<int>((static_cast<unsigned>(t) * magic) >> 22) : t / side;
             vv[k] = vr - radius;
             uu[k] = t - vr * side - radius;
             const int X = rx + uu[k], Y = ry + vv[k];
             on[k] = t < count && X >= 0 && X < w && Y >= 0 && Y < h;
             xn[k] = xp[k] = yn[k] = yp[k] = 0.f;
-            if (on[k])
+            if (on[k] && interior)
+            {
+              const float* p = G + static_cast<size_t>(Y) * pitch + X;
+              xn[k] = __ldg(p + 1);
+              xp[k] = __ldg(p - 1);
+              yn[k] = __ldg(p + pitch);
+              yp[k] = __ldg(p - pitch);
+            }
+            else if (on[k])
             {
               // Gradient functor: central differences, one-sided at the borders (Differential.hpp:46-61)
               const float* row = G + static_cast<size_t>(Y) * pitch;
@@ -101,8 +113,9 @@ namespace sb {
           {
             if (!on[k])
               continue;
-            const float gx = __fdiv_rn(__fsub_rn(xn[k], xp[k]), 2.f);
-            const float gy = __fdiv_rn(__fsub_rn(yn[k], yp[k]), 2.f);
+            // "/ 2" as "* 0.5": the same bits (an exact scaling by a power of two), a tenth of the instructions
+            const float gx = __fmul_rn(__fsub_rn(xn[k], xp[k]), 0.5f);
+            const float gy = __fmul_rn(__fsub_rn(yn[k], yp[k]), 0.5f);
             const float mag = __fmul_rn(2.f, __fsqrt_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy))));
             float ori = atan2f(gy, gx);
             ori = ori < 0.f ? __fadd_rn(ori, kTwoPi) : ori;
