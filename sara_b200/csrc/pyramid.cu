@@ -1,7 +1,8 @@
 // Generic pyramid kernels: one separable Gaussian stage (row pass, column pass,
 // optional DoG epilogue) for ANY tap count, nearest-neighbour downscale and the
 // double-precision bilinear enlarge.  These serve every parameter set; the
-// default SIFT schedule runs on the fused octave kernel in pyramid_fused.cu.
+// default SIFT schedule runs on march_kernel (pyramid_march.cu) for the large
+// octaves, octave_head_kernel / tail_octaves_kernel (below) for the small ones.
 //
 // Bit-exactness contract (checked against the oracle with memcmp): this file is
 // compiled with -fmad=false; every tap is a separate multiply and add, taps are
