@@ -435,12 +435,10 @@ namespace sb {
         };
 
         // The kept pixels of the bounding square [-rounded_r, rounded_r]^2, in raster order.  The test of
-        // SIFT.hpp:84-110 (-1 < pos < 4 on both axes, pos = T (u, v) + 1.5) is, in float arithmetic too, a
-        // conjunction of four conditions that are MONOTONE in u (every rounded operation is monotone), so on a
-        // row the kept pixels form exactly one interval.  A lane works out the interval of one row: first from
-        // the inverse inequalities, widened by a pixel on both sides, then it moves both ends inwards until the
-        // exact float test accepts them.  The warp then copies the intervals into its queue 32 pixels at a
-        // time -- no per-pixel test, no ballot -- and about half of the square is never visited.
+        // SIFT.hpp:84-110 (-1 < pos < 4 on both axes, pos = T (u, v) + 1.5) is linear in u, so on a row the
+        // kept pixels form one interval: a lane works out the interval of one row from the inverse
+        // inequalities, widened by a pixel on both sides (the exact float test below has the last word),
+        // and the warp then visits only those pixels -- about half of the square -- 32 at a time.
         int q_n = 0;  // entries waiting in the queue (< 96 between rounds)
         const int u_min = max(-rounded_r, -rx), u_max = min(rounded_r, w - 1 - rx);
         for (int v0 = -rounded_r; v0 <= rounded_r; v0 += 32)
@@ -451,8 +449,7 @@ namespace sb {
             if (v <= rounded_r && Y >= 0 && Y < h)
             {
               const float fv = static_cast<float>(v);
-              const float tx = __fmul_rn(T01, fv), ty = __fmul_rn(T11, fv);
-              const float bx = tx + 1.5f, by = ty + 1.5f;
+              const float bx = __fmul_rn(T01, fv) + 1.5f, by = __fmul_rn(T11, fv) + 1.5f;
               float lo = -1e9f, hi = 1e9f;
               if (fabsf(T00) > 1e-12f)
               {
@@ -472,17 +469,6 @@ namespace sb {
               {
                 my_lo = max(u_min, static_cast<int>(floorf(lo)) - 1);
                 my_hi = min(u_max, static_cast<int>(ceilf(hi)) + 1);
-                // the reference's test, operation for operation
-                auto kept = [&](int u) {
-                  const float fu = static_cast<float>(u);
-                  const float px = __fadd_rn(__fadd_rn(__fmul_rn(T00, fu), tx), 1.5f);
-                  const float py = __fadd_rn(__fadd_rn(__fmul_rn(T10, fu), ty), 1.5f);
-                  return fminf(px, py) > -1.f && fmaxf(px, py) < 4.f;
-                };
-                while (my_lo <= my_hi && !kept(my_lo))
-                  ++my_lo;
-                while (my_lo <= my_hi && !kept(my_hi))
-                  --my_hi;
               }
             }
           }
@@ -490,13 +476,20 @@ namespace sb {
           for (int rrow = 0; rrow < n_rows; ++rrow)
           {
             const int ulo = __shfl_sync(0xffffffffu, my_lo, rrow), uhi = __shfl_sync(0xffffffffu, my_hi, rrow);
-            const int vhi = (v0 + rrow) << 16;
+            const int v = v0 + rrow;
+            const float fv = static_cast<float>(v);
+            const float tx = __fmul_rn(T01, fv), ty = __fmul_rn(T11, fv);
             for (int ub = ulo; ub <= uhi; ub += 32)
             {
               const int u = ub + lane;
-              if (u <= uhi)
-                queue[q_n + lane] = (u & 0xffff) | vhi;
-              q_n += min(32, uhi - ub + 1);
+              const float fu = static_cast<float>(u);
+              const float px = __fadd_rn(__fadd_rn(__fmul_rn(T00, fu), tx), 1.5f);
+              const float py = __fadd_rn(__fadd_rn(__fmul_rn(T10, fu), ty), 1.5f);
+              const bool keep = u <= uhi && fminf(px, py) > -1.f && fmaxf(px, py) < 4.f;
+              const unsigned m = __ballot_sync(0xffffffffu, keep);
+              if (keep)
+                queue[q_n + __popc(m & ((1u << lane) - 1u))] = (u & 0xffff) | (v << 16);
+              q_n += __popc(m);
               __syncwarp();
               if (q_n >= 96)
               {
