@@ -236,7 +236,11 @@ namespace sb {
     {
       const float ax = fabsf(x), ay = fabsf(y);
       const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-      const float a = mx > 0.f ? __fdividef(mn, mx) : 0.f;
+      // mn / mx by the approximate reciprocal (gradient differences are far from the denormal range, where
+      // the flush-to-zero form would give inf and the guard below 0)
+      float rcp;
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(mx));
+      const float a = mx > 1e-30f ? __fmul_rn(mn, rcp) : 0.f;
       const float s = __fmul_rn(a, a);
       float r = __fmaf_rn(s, -0.0117212f, 0.05265332f);
       r = __fmaf_rn(r, s, -0.11643287f);
@@ -363,7 +367,11 @@ namespace sb {
           Weights w;
           float px = __fadd_rn(__fmul_rn(T00, sm.fu), __fmul_rn(T01, sm.fv));
           float py = __fadd_rn(__fmul_rn(T10, sm.fu), __fmul_rn(T11, sm.fv));
-          const float weight = __expf(__fmul_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), -0.125f));
+          // exp(-(px^2 + py^2) / 8) = 2^(-(px^2 + py^2) * log2(e) / 8); the argument stays above -3, no flush needed
+          float weight;
+          asm("ex2.approx.ftz.f32 %0, %1;"
+              : "=f"(weight)
+              : "f"(__fmul_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), -0.180336880f)));
           px = __fadd_rn(px, 1.5f);
           py = __fadd_rn(py, 1.5f);
           const float dx = __fsub_rn(sm.xn, sm.xp), dy = __fsub_rn(sm.yn, sm.yp);
