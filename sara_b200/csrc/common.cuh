@@ -94,6 +94,10 @@ namespace sb {
   // Marching scatter-form kernel (pyramid_march.cu): same contract as launch_stage, fewer fp32
   // instructions (symmetric taps share their products) and no shared-memory window loads.
   bool march_kernel_supported(const Taps& taps);
+  // Segment height of the layers that cannot fill the machine, for the launches that follow on this host
+  // thread: `throughput` = several frames in flight (fewer, taller segments: less warm-up work), otherwise
+  // the shortest chain for a lone frame.
+  void set_march_schedule(bool throughput);
   bool launch_march(const float* src, int src_pitch, float* dst, float* dog, float* nextG, int w, int h,
                     int pitch, int nw, int nh, int npitch, const Taps& taps, cudaStream_t st);
   bool downscale_is_even_sampling(int sw, int sh, int dw, int dh);

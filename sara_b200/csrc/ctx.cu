@@ -423,6 +423,8 @@ namespace {
     if (rc)
       return rc;
     S.stream = st;
+    // a context made for several frames in flight trades a lone frame's latency for machine time
+    set_march_schedule(ctx->slots.size() >= 4);
     S.pyramid_launches = 0;
     S.extra_launches = 0;
     S.extra_launches_pre = 0;

@@ -452,6 +452,8 @@ namespace sb {
       }
     }
 
+    thread_local int t_short_blocks = 4;
+
     template <int K>
     bool launch(const float* src, int src_pitch, float* dst, float* dog, float* nextG, int w, int h, int pitch, int nw,
                 int nh, int npitch, const Taps& taps, cudaStream_t st)
@@ -503,12 +505,23 @@ namespace sb {
       // Segments.  Every segment pays 2c warm-up rows and works in 32-row blocks.  A large layer
       // is cut into as many CTAs as the machine holds at once (148 SMs x 2 resident CTAs) and no
       // more -- a second wave would only add warm-up rows.  A small layer cannot fill the machine;
-      // there the launch is latency bound (a CTA walks its blocks one after the other), so it gets
-      // short segments of 64 - 2c output rows: exactly two blocks each.
+      // it gets segments of a whole number of blocks (warm-up included): 4 blocks when a frame runs
+      // alone (measured best for its latency), 6 when several frames are in flight (a quarter less
+      // machine time for octave 1 of a 4K frame than the two-block segments of earlier versions).
       const int n_strips = (w + TX - 1) / TX;
       const int slots = 148 * per_sm;
-      const int hy_short = 2 * R - 2 * S::c;
+      // Short-segment rule, in 32-row blocks through the pipeline (set_march_schedule): taller segments
+      // waste fewer warm-up rows (machine time), shorter ones finish a lone launch sooner (latency).
+      static const int env_blocks = [] {
+        const char* e = getenv("SARA_B200_MARCH_BLOCKS");
+        return e && atoi(e) > 0 ? atoi(e) : 0;
+      }();
+      const int short_blocks = env_blocks > 0 ? env_blocks : t_short_blocks;
+      const int hy_short = short_blocks * R - 2 * S::c;
       int best_segs = std::max(1, std::min((h + hy_short - 1) / hy_short, slots / n_strips));
+      // a layer that would fill most of the machine anyway gets exactly one CTA per slot
+      if (best_segs * n_strips * 100 >= slots * 60)
+        best_segs = std::max(1, slots / n_strips);
       static const int force = [] {
         const char* e = getenv("SARA_B200_MARCH_SEGS");
         return e ? atoi(e) : 0;
@@ -530,6 +543,8 @@ namespace sb {
     }
 
   }  // namespace march
+
+  void set_march_schedule(bool throughput) { march::t_short_blocks = throughput ? 6 : 4; }
 
   bool march_kernel_supported(const Taps& taps)
   {
