@@ -140,3 +140,29 @@ def test_8k_frame_pyramid_implementations_agree():
         assert c.num_octaves() == 11 and len(kl) >= 0
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("size", [(3840, 2160), (1920, 1080), (1300, 420)])
+def test_latency_and_throughput_schedules_agree(size):
+    """A context made for several frames in flight cuts the layers that cannot fill the machine into
+    fewer, taller segments (set_march_schedule in csrc/pyramid_march.cu); the segment height must
+    not show in a single bit of the pyramid, nor in the keypoints and descriptors."""
+    w, h = size
+    img = S.tex(w, h, 97)
+    pp = sb.ImagePyramidParams(first_octave_index=0)
+    res = []
+    for slots in (1, 4):
+        c = sb.SiftContext(w, h, max_keypoints=131072, num_slots=slots)
+        try:
+            kl = c.compute_sift_keypoints(img, pp)
+            G, D = _layers(c)
+            res.append((kl, G, D))
+        finally:
+            c.close()
+    (ka, Ga, Da), (kb, Gb, Db) = res
+    assert len(ka) == len(kb) > 0
+    for o in range(len(Ga)):
+        for a, b in zip(Ga[o] + Da[o], Gb[o] + Db[o]):
+            assert a.tobytes() == b.tobytes()
+    assert ka.features.tobytes() == kb.features.tobytes()
+    assert ka.descriptors.tobytes() == kb.descriptors.tobytes()
