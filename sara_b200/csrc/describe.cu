@@ -363,33 +363,53 @@ namespace sb {
           int a[8];  // float offsets into the lane's histogram copy
           float v[8];
         };
-        auto weights = [&](const Sample& sm) {
-          Weights w;
+        // ... in two steps: geom() is everything that depends on the sample's POSITION only and runs for all
+        // three samples of a lane while their gradient loads are in flight; finish() needs the loaded values.
+        struct Geom
+        {
+          float weight, xfrac, yfrac, a00, a01, a10, a11;
+          int cell;
+          bool x1, y1;
+        };
+        auto geom = [&](const Sample& sm) {
+          Geom g;
           float px = __fadd_rn(__fmul_rn(T00, sm.fu), __fmul_rn(T01, sm.fv));
           float py = __fadd_rn(__fmul_rn(T10, sm.fu), __fmul_rn(T11, sm.fv));
           // exp(-(px^2 + py^2) / 8) = 2^(-(px^2 + py^2) * log2(e) / 8); the argument stays above -3, no flush needed
-          float weight;
           asm("ex2.approx.ftz.f32 %0, %1;"
-              : "=f"(weight)
+              : "=f"(g.weight)
               : "f"(__fmul_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), -0.180336880f)));
           px = __fadd_rn(px, 1.5f);
           py = __fadd_rn(py, 1.5f);
+          // std::modf truncates toward zero (quirk N6): for pos in (-1, 0) the integer part is 0,
+          // the weight of cell 0 is 1 - frac > 1 and the one of cell 1 is frac < 0.
+          const int xi = static_cast<int>(px), yi = static_cast<int>(py);
+          g.xfrac = __fsub_rn(px, static_cast<float>(xi));
+          g.yfrac = __fsub_rn(py, static_cast<float>(yi));
+          // (xi, yi) in [0, 3]; the +1 neighbours exist for xi, yi < 3
+          const float wy0 = __fsub_rn(1.f, g.yfrac), wx0 = __fsub_rn(1.f, g.xfrac);
+          g.x1 = xi < 3;
+          g.y1 = yi < 3;
+          g.cell = ((4 * yi + xi) * 8) * DESC_NC + lcopy;
+          g.a00 = __fmul_rn(wy0, wx0);
+          g.a01 = __fmul_rn(wy0, g.xfrac);
+          g.a10 = __fmul_rn(g.yfrac, wx0);
+          g.a11 = __fmul_rn(g.yfrac, g.xfrac);
+          return g;
+        };
+        auto finish = [&](const Sample& sm, const Geom& g) {
+          Weights w;
           const float dx = __fsub_rn(sm.xn, sm.xp), dy = __fsub_rn(sm.yn, sm.yp);
           const float mag = approx_sqrt(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));  // = 2 |(dx, dy) / 2|
           float ori = __fsub_rn(fast_atan2(dy, dx), theta);
           ori = ori < 0.f ? __fadd_rn(ori, kTwoPi) : ori;
           ori = __fmul_rn(ori, 1.27323954f);  // 8 / (2 pi)
-          // std::modf truncates toward zero (quirk N6): for pos in (-1, 0) the integer part is 0,
-          // the weight of cell 0 is 1 - frac > 1 and the one of cell 1 is frac < 0.
-          const int xi = static_cast<int>(px), yi = static_cast<int>(py), oi = static_cast<int>(ori);
-          const float xfrac = __fsub_rn(px, static_cast<float>(xi)), yfrac = __fsub_rn(py, static_cast<float>(yi));
+          const int oi = static_cast<int>(ori);
           const float ofrac = __fsub_rn(ori, static_cast<float>(oi));
-          const float wm = __fmul_rn(weight, mag);
+          const float wm = __fmul_rn(g.weight, mag);
           const float wo1 = __fmul_rn(ofrac, wm), wo0 = __fsub_rn(wm, wo1);
-          // (xi, yi) in [0, 3]; the +1 neighbours exist for xi, yi < 3
-          const float wy0 = __fsub_rn(1.f, yfrac), wx0 = __fsub_rn(1.f, xfrac);
-          const bool x1 = xi < 3, y1 = yi < 3;
-          const int cell = ((4 * yi + xi) * 8) * DESC_NC + lcopy;
+          const bool x1 = g.x1, y1 = g.y1;
+          const int cell = g.cell;
           const int o0 = (oi & 7) * DESC_NC, o1 = ((oi + 1) & 7) * DESC_NC;
           const int cx = cell + 8 * DESC_NC, cy = cell + 32 * DESC_NC;
           const int scratch = 128 * DESC_NC + lcopy;
@@ -401,16 +421,14 @@ namespace sb {
           w.a[5] = y1 ? cy + o1 : scratch + 5 * DESC_NC;
           w.a[6] = (x1 && y1) ? cy + 8 * DESC_NC + o0 : scratch + 6 * DESC_NC;
           w.a[7] = (x1 && y1) ? cy + 8 * DESC_NC + o1 : scratch + 7 * DESC_NC;
-          const float a00 = __fmul_rn(wy0, wx0), a01 = __fmul_rn(wy0, xfrac);
-          const float a10 = __fmul_rn(yfrac, wx0), a11 = __fmul_rn(yfrac, xfrac);
-          w.v[0] = __fmul_rn(a00, wo0);
-          w.v[1] = __fmul_rn(a00, wo1);
-          w.v[2] = __fmul_rn(a01, wo0);
-          w.v[3] = __fmul_rn(a01, wo1);
-          w.v[4] = __fmul_rn(a10, wo0);
-          w.v[5] = __fmul_rn(a10, wo1);
-          w.v[6] = __fmul_rn(a11, wo0);
-          w.v[7] = __fmul_rn(a11, wo1);
+          w.v[0] = __fmul_rn(g.a00, wo0);
+          w.v[1] = __fmul_rn(g.a00, wo1);
+          w.v[2] = __fmul_rn(g.a01, wo0);
+          w.v[3] = __fmul_rn(g.a01, wo1);
+          w.v[4] = __fmul_rn(g.a10, wo0);
+          w.v[5] = __fmul_rn(g.a10, wo1);
+          w.v[6] = __fmul_rn(g.a11, wo0);
+          w.v[7] = __fmul_rn(g.a11, wo1);
           return w;
         };
         // the 8 bin updates of one sample, for the lanes whose turn it is: all loads, then all stores
@@ -431,7 +449,8 @@ namespace sb {
           const Sample a = fetch(queue[lane], on0);
           const Sample b = fetch(queue[lane + 32], on1);
           const Sample c = fetch(queue[lane + 64], on2);
-          const Weights wa = weights(a), wb = weights(b), wc = weights(c);
+          const Geom ga = geom(a), gb = geom(b), gc = geom(c);
+          const Weights wa = finish(a, ga), wb = finish(b, gb), wc = finish(c, gc);
 #pragma unroll
           for (int ph = 0; ph < 32 / DESC_NC; ++ph)
           {
