@@ -18,6 +18,9 @@
  * serialised by the caller; different ctxs are independent.  A ctx owns
  * `num_slots` independent frame slots (device arena + stream each) so that
  * several frames can be in flight: enqueue on slot i, collect slot i later.
+ * A ctx with four or more slots cuts the small pyramid layers into fewer,
+ * taller segments (less machine time per frame, a slightly longer lone frame);
+ * the results are bit-identical.
  *
  * There is NO CPU fallback: if no CUDA device is usable sara_b200_create fails
  * with SARA_B200_ERR_CUDA.
