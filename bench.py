@@ -194,7 +194,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args):
@@ -244,8 +244,6 @@ def run_ours(args):
             nv.nvmlDeviceSetCpuAffinity(nv.nvmlDeviceGetHandleByIndex(local_rank))
         except Exception:
             pass
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner on STDOUT, where the JSON line goes
         dist.init_process_group("nccl", device_id=dev)
 
     pp = sb.ImagePyramidParams(first_octave_index=0)
@@ -524,13 +522,33 @@ def run_ours(args):
             "clocks": clocks, "roofline": roofline, "stage_ms_per_frame": stage_ms, "cpu_baseline": cpu_baseline,
             "matching": matching, "timed_region_s": max_secs, "wall_s": wall,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    # Nothing but the JSON line may reach stdout: NCCL prints its version banner there (at NCCL_DEBUG =
+    # VERSION, WARN or INFO), libraries may chat.  File descriptor 1 is pointed at stderr for the whole run
+    # and the line is written to a duplicate of the original stdout.
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
