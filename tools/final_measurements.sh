@@ -1,3 +1,5 @@
+# The measurement pass behind profiles/r02_*: GPU tests, smoke, bench (both arms), ncu launch lists, one --set full capture.
+#   gpurun --timeout 1500 -- "bash tools/final_measurements.sh"
 timeout 500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 timeout 100 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
 timeout 600 python bench.py > gpurun_out/r2_bench18.json 2> gpurun_out/r2_bench18.err; tail -c 300 gpurun_out/r2_bench18.err
