@@ -166,3 +166,22 @@ def test_latency_and_throughput_schedules_agree(size):
             assert a.tobytes() == b.tobytes()
     assert ka.features.tobytes() == kb.features.tobytes()
     assert ka.descriptors.tobytes() == kb.descriptors.tobytes()
+
+
+def test_eight_4k_frames_in_flight_equal_the_lone_frames():
+    """The bench's regime: eight 4K frames in flight on eight streams (kernels of different frames share the
+    SMs, the side streams of all slots are busy).  Every frame must come out exactly as it does alone."""
+    pp = sb.ImagePyramidParams(first_octave_index=0)
+    imgs = [S.tex(3840, 2160, 500 + i) for i in range(4)]
+    c = sb.SiftContext(3840, 2160, max_keypoints=131072, num_slots=8)
+    try:
+        lone = [c.compute_sift_keypoints(im, pp) for im in imgs]
+        for _ in range(3):
+            for slot in range(8):
+                c.enqueue(slot, imgs[slot % 4], pp)
+            for slot in range(8):
+                kl = c.collect(slot)
+                assert kl.features.tobytes() == lone[slot % 4].features.tobytes()
+                assert kl.descriptors.tobytes() == lone[slot % 4].descriptors.tobytes()
+    finally:
+        c.close()
