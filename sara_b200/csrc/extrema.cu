@@ -39,7 +39,8 @@ namespace sb {
     // separate, rarely executed routine.  Nothing is staged in shared memory and no two warps
     // talk to each other.
     constexpr int CLS_W = 120;     // pixels a warp classifies per row
-    constexpr int CLS_SEG = 32;    // rows per warp
+    constexpr int CLS_SEG = 8;     // rows per warp: short segments = several waves of warps at 5 blocks per SM (measured: 32
+                                   // rows 54.6 us, 16 rows 48.4, 8 rows 44.6 for octave 0 of a 4K frame; 2 halo rows per segment)
     constexpr int CLS_MAXL = 5;    // DoG layers of the default schedule (register-resident path)
 
     struct ClassifyTiles
@@ -96,7 +97,7 @@ namespace sb {
     }
 
     template <int NL>  // DoG layers per octave (n_scales - 1); layers 1 .. NL - 2 are streamed and classified
-    __global__ void __launch_bounds__(128, 4)
+    __global__ void __launch_bounds__(128, 5)
         classify_sweep_kernel(const __grid_constant__ PyramidDesc P, const __grid_constant__ ClassifyTiles Tl,
                               const ExtremaParams ep)
     {
@@ -1029,13 +1030,18 @@ namespace sb {
       return launches;
     }
     ClassifyTiles T{};
-    // A launch that covers octave 0 fills the machine with 32-row segments; the smaller octaves alone are a
-    // latency-bound launch (a warp walks its rows one after the other) and get short segments instead.
+    // Short segments for every launch: octave 0 then runs as several waves of warps at 5 blocks per SM
+    // (better latency hiding than one wave of 32-row warps), the smaller octaves alone are a latency-bound
+    // launch (a warp walks its rows one after the other).
     static const int seg_small = [] {
       const char* e = getenv("SARA_B200_CLS_SEG_SMALL");
       return e ? std::max(4, atoi(e)) : 8;
     }();
-    T.seg = o_lo == 0 ? CLS_SEG : seg_small;
+    static const int seg_big = [] {
+      const char* e = getenv("SARA_B200_CLS_SEG");
+      return e ? std::max(4, atoi(e)) : CLS_SEG;
+    }();
+    T.seg = o_lo == 0 ? seg_big : seg_small;
     for (int o = 0; o < P.n_octaves; ++o)
     {
       const bool in = o >= o_lo && o < o_hi;
