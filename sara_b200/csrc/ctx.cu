@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -94,6 +95,25 @@ namespace {
 
   }  // namespace
 
+// Uploads from PAGEABLE host memory (what a Sara caller's ImageView<float> points at).  cudaMemcpyAsync stages such
+// a copy through the driver's bounce buffer on the calling thread (about 12 GB/s: 2.7 ms for a 4K float frame, most
+// of the drop-in call); here kThreads host threads each copy a slice of the frame into their own pair of pinned
+// chunks and queue the DMA on their own stream, so the host-side copy runs on several cores and overlaps with the
+// transfers.  Pinned and device-resident sources never come here.
+struct HostStager
+{
+  static constexpr int kThreads = 4;
+  static constexpr size_t kChunk = size_t(2) << 20;
+  static constexpr size_t kMinBytes = size_t(4) << 20;
+  unsigned char* pinned = nullptr;  // kThreads x 2 chunks
+  cudaStream_t stream[kThreads] = {};
+  cudaEvent_t chunk_done[kThreads][2] = {};
+  bool chunk_used[kThreads][2] = {};
+  cudaEvent_t done[kThreads] = {};
+  cudaEvent_t start = nullptr;
+  bool ready = false, broken = false;
+};
+
 struct sara_b200_ctx
 {
   int device = 0;
@@ -111,6 +131,7 @@ struct sara_b200_ctx
   sb::LaplaceTable* d_laplace = nullptr;  // constants of select_laplace_scale (Hessian-Laplace), uploaded per call
   unsigned char* match_io = nullptr;  // device copies of host descriptors + result buffers of the matcher
   size_t match_io_bytes = 0;
+  HostStager stager;
   char err[512] = "";
 };
 
@@ -134,6 +155,87 @@ namespace {
       return fail(ctx, e_ == cudaErrorMemoryAllocation ? SARA_B200_ERR_OOM : SARA_B200_ERR_CUDA,  \
                   "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);     \
   } while (0)
+
+  bool is_pageable(const void* p)
+  {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess)
+    {
+      cudaGetLastError();
+      return false;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+  }
+
+  // Host -> device copy of `bytes` ordered on `st`, whatever kind of host memory `src` is.
+  int upload(sara_b200_ctx* ctx, void* dst, const void* src, size_t bytes, cudaStream_t st)
+  {
+    HostStager& H = ctx->stager;
+    if (bytes < HostStager::kMinBytes || H.broken || !is_pageable(src))
+    {
+      CU(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+      return 0;
+    }
+    constexpr int T = HostStager::kThreads;
+    constexpr size_t CH = HostStager::kChunk;
+    if (!H.ready)
+    {
+      bool ok = cudaHostAlloc(reinterpret_cast<void**>(&H.pinned), T * 2 * CH, cudaHostAllocDefault) == cudaSuccess &&
+                cudaEventCreateWithFlags(&H.start, cudaEventDisableTiming) == cudaSuccess;
+      for (int t = 0; t < T && ok; ++t)
+        ok = cudaStreamCreateWithFlags(&H.stream[t], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&H.done[t], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&H.chunk_done[t][0], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&H.chunk_done[t][1], cudaEventDisableTiming) == cudaSuccess;
+      if (!ok)
+      {
+        cudaGetLastError();
+        H.broken = true;  // (whatever was created is released by sara_b200_destroy)
+        CU(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+        return 0;
+      }
+      H.ready = true;
+    }
+    // the destination may still be read by work queued on `st`
+    CU(ctx, cudaEventRecord(H.start, st));
+    const size_t part = ((bytes + T - 1) / T + 255) & ~size_t(255);
+    cudaError_t err[T];
+    auto work = [&](int t) {
+      err[t] = cudaSetDevice(ctx->device);
+      if (err[t] == cudaSuccess)
+        err[t] = cudaStreamWaitEvent(H.stream[t], H.start, 0);
+      const size_t lo = std::min(bytes, part * t), hi = std::min(bytes, part * (t + 1));
+      int b = 0;
+      for (size_t off = lo; off < hi && err[t] == cudaSuccess; off += CH, b ^= 1)
+      {
+        const size_t n = std::min(CH, hi - off);
+        unsigned char* stage = H.pinned + (static_cast<size_t>(t) * 2 + b) * CH;
+        if (H.chunk_used[t][b])
+          err[t] = cudaEventSynchronize(H.chunk_done[t][b]);  // the previous DMA out of this chunk
+        if (err[t] != cudaSuccess)
+          break;
+        memcpy(stage, static_cast<const unsigned char*>(src) + off, n);
+        err[t] = cudaMemcpyAsync(static_cast<unsigned char*>(dst) + off, stage, n, cudaMemcpyHostToDevice, H.stream[t]);
+        if (err[t] == cudaSuccess)
+          err[t] = cudaEventRecord(H.chunk_done[t][b], H.stream[t]);
+        H.chunk_used[t][b] = true;
+      }
+      if (err[t] == cudaSuccess)
+        err[t] = cudaEventRecord(H.done[t], H.stream[t]);
+    };
+    std::thread th[T - 1];
+    for (int t = 1; t < T; ++t)
+      th[t - 1] = std::thread(work, t);
+    work(0);
+    for (int t = 1; t < T; ++t)
+      th[t - 1].join();
+    for (int t = 0; t < T; ++t)
+      if (err[t] != cudaSuccess)
+        return fail(ctx, SARA_B200_ERR_CUDA, "staged upload failed: %s", cudaGetErrorString(err[t]));
+    for (int t = 0; t < T; ++t)
+      CU(ctx, cudaStreamWaitEvent(st, H.done[t], 0));
+    return 0;
+  }
 
   // The API calls run on the context's device and leave the caller's current device as it was.
   struct DeviceGuard
@@ -440,7 +542,11 @@ namespace {
       if (!on_device)
       {
         if (!skip_upload)
-          CU(ctx, cudaMemcpyAsync(S.d_u8, image_any, u8_bytes, cudaMemcpyHostToDevice, st));
+        {
+          const int urc = upload(ctx, S.d_u8, image_any, u8_bytes, st);
+          if (urc)
+            return urc;
+        }
         d_u8 = S.d_u8;
       }
       if (u8_channels == 3)
@@ -453,7 +559,11 @@ namespace {
     else if (!on_device)
     {
       if (!skip_upload)
-        CU(ctx, cudaMemcpyAsync(S.d_img, image, sizeof(float) * w * h, cudaMemcpyHostToDevice, st));
+      {
+        const int urc = upload(ctx, S.d_img, image, sizeof(float) * w * h, st);
+        if (urc)
+          return urc;
+      }
       d_src = S.d_img;
     }
     if (prof)
@@ -972,6 +1082,24 @@ void sara_b200_destroy(sara_b200_ctx* ctx)
     if (S.own_stream)
       cudaStreamDestroy(S.own_stream);
   }
+  {
+    HostStager& H = ctx->stager;
+    for (int t = 0; t < HostStager::kThreads; ++t)
+    {
+      if (H.stream[t])
+      {
+        cudaStreamSynchronize(H.stream[t]);
+        cudaStreamDestroy(H.stream[t]);
+      }
+      for (cudaEvent_t e : {H.done[t], H.chunk_done[t][0], H.chunk_done[t][1]})
+        if (e)
+          cudaEventDestroy(e);
+    }
+    if (H.start)
+      cudaEventDestroy(H.start);
+    if (H.pinned)
+      cudaFreeHost(H.pinned);
+  }
   cudaFree(ctx->d_gray_lut);
   cudaFree(ctx->scratch);
   cudaFree(ctx->match_io);
@@ -1186,10 +1314,10 @@ static int sift_enqueue_impl(sara_b200_ctx* ctx, int slot, const void* image, in
   fg->last_use = ++S.graph_clock;
   if (!on_device)
   {
-    if (u8_channels > 0)
-      CU(ctx, cudaMemcpyAsync(S.d_u8, image, static_cast<size_t>(w) * h * u8_channels, cudaMemcpyHostToDevice, st));
-    else
-      CU(ctx, cudaMemcpyAsync(S.d_img, image, sizeof(float) * w * h, cudaMemcpyHostToDevice, st));
+    const int urc = u8_channels > 0 ? upload(ctx, S.d_u8, image, static_cast<size_t>(w) * h * u8_channels, st)
+                                    : upload(ctx, S.d_img, image, sizeof(float) * w * h, st);
+    if (urc)
+      return urc;
   }
   CU(ctx, cudaGraphLaunch(fg->exec, st));
   S.has_keypoints = true;

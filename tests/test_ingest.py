@@ -91,3 +91,39 @@ def test_sift_from_8bit_frames(channels):
             ctx.enqueue_u8(0, np.zeros((4, 4, 2), np.uint8), pp)
     finally:
         ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("size", [(3840, 2160), (3001, 2003), (1920, 1080)])
+def test_pageable_frames_are_staged_without_changing_a_bit(size):
+    """Frames in ordinary (pageable) host memory of 4 MiB or more are uploaded by the multi-threaded pinned-chunk
+    stager (HostStager in csrc/ctx.cu): same results as the same frame resident on the device, on repeated calls
+    (chunk reuse), with and without CUDA graphs, for float and 8-bit frames, for sizes that do not divide into
+    the threads' parts or the 2 MiB chunks."""
+    import torch
+
+    import sara_b200 as sb
+    from sara_b200 import synthetic as S
+
+    w, h = size
+    img = S.tex(w, h, 31)
+    u8 = np.clip(np.rint(np.stack([img, img[::-1], img[:, ::-1]], axis=2) * 255), 0, 255).astype(np.uint8)
+    pp = sb.ImagePyramidParams(first_octave_index=0)
+    ctx = sb.SiftContext(w, h, max_keypoints=131072, num_slots=2)
+    try:
+        want = ctx.compute_sift_keypoints(torch.from_numpy(img).cuda(), pp)
+        want8 = None
+        ctx.enqueue_u8(1, torch.from_numpy(u8).cuda(), pp)
+        want8 = ctx.collect(1)
+        assert len(want) > 100 and len(want8) > 100
+        for graphs in (True, False):
+            ctx.set_graphs(graphs)
+            for _ in range(3):
+                got = ctx.compute_sift_keypoints(img, pp)
+                assert got.features.tobytes() == want.features.tobytes()
+                assert got.descriptors.tobytes() == want.descriptors.tobytes()
+                got8 = ctx.compute_sift_keypoints_u8(u8, pp)
+                assert got8.features.tobytes() == want8.features.tobytes()
+                assert got8.descriptors.tobytes() == want8.descriptors.tobytes()
+    finally:
+        ctx.close()
