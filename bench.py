@@ -344,6 +344,22 @@ def run_ours(args):
     h_frames = [torch.from_numpy(f).pin_memory() for f in frames]
     e2e = e2e_leg(h_frames, 0)
     e2e["input"] = "float32 gray frames in pinned host memory (the C ABI's ImageView<float> contract)"
+    # What the host link alone allows: the step's float frames copied host -> device on the same streams, no
+    # compute.  When this takes as long as the e2e step, the e2e figure is the PCIe figure, not the kernels'.
+    d_sink = [torch.empty(H4K, W4K, dtype=torch.float32, device=dev) for _ in range(NS)]
+
+    def copies_only(steps):
+        for j in range(steps * F):
+            with torch.cuda.stream(streams[j % NS]):
+                d_sink[j % NS].copy_(h_frames[j % F], non_blocking=True)
+        return 0
+
+    copies_only(1)
+    _, c_ev, c_wall = timed(copies_only, args.steps)
+    c_ms = 1e3 * max(c_ev, c_wall) / args.steps
+    e2e["h2d_only"] = {"ms_per_step": c_ms, "GB/s_per_gpu": F * W4K * H4K * 4 / (c_ms * 1e-3) / 1e9,
+                       "how": "the step's pinned float frames copied to the device on the same streams, nothing else running"}
+    del d_sink
     u8_gray = [np.clip(np.rint(f * 255.0), 0, 255).astype(np.uint8) for f in frames]
     h_gray8 = [torch.from_numpy(g).pin_memory() for g in u8_gray]
     e2e_gray8 = e2e_leg(h_gray8, 1)
