@@ -1,0 +1,164 @@
+"""A second, independent restatement of the gradient / orientation-histogram / descriptor stage, written in
+vectorised float64 numpy straight from the reference sources (not from oracle/sift_oracle.cpp), checked against the
+oracle.  The reference's own tests pin this stage only by shape and by a single-gradient histogram
+(test_featuredescriptors_sift.cpp, test_featuredescriptors_orientation.cpp), so without this file a slip in the
+oracle's bin indexing, weights or window geometry would go unnoticed by every parity test (the CUDA kernels are
+compared with the oracle).  float64 against float32: values agree to rounding, except that a sample sitting on the
+edge of the rotated grid or on a bin boundary can fall on the other side -- hence the small tolerances below.
+
+  gradient (central differences, one-sided halves at the borders)   ImageProcessing/Differential.hpp:46-61
+  polar form (2 |g|, atan2)                                          FeatureDescriptors/Orientation.cpp:45-51
+  compute_orientation_histogram                                      FeatureDescriptors/Orientation.hpp:90-135
+  ComputeSIFTDescriptor<4, 8>::operator(), accumulate, normalize     FeatureDescriptors/SIFT.hpp:62-145, 204-258
+"""
+import numpy as np
+
+from oracle import oracle as O
+from sara_b200 import synthetic as S
+
+
+def int_round(x):
+    """DO::Sara::int_round: int(round(x)), round half away from zero (Core/Math/UsualFunctions.hpp)."""
+    return int(np.floor(abs(x) + 0.5) * np.sign(x))
+
+
+def gradient_polar64(img):
+    f = img.astype(np.float64)
+    gx = np.empty_like(f)
+    gy = np.empty_like(f)
+    gx[:, 1:-1] = (f[:, 2:] - f[:, :-2]) / 2
+    gx[:, 0] = (f[:, 1] - f[:, 0]) / 2
+    gx[:, -1] = (f[:, -1] - f[:, -2]) / 2
+    gy[1:-1, :] = (f[2:, :] - f[:-2, :]) / 2
+    gy[0, :] = (f[1, :] - f[0, :]) / 2
+    gy[-1, :] = (f[-1, :] - f[-2, :]) / 2
+    return 2 * np.hypot(gx, gy), np.arctan2(gy, gx)
+
+
+def orientation_histogram64(mag, ori, x, y, s, trunc=3.0, blur=1.5, n=36):
+    h, w = mag.shape
+    rx, ry = int_round(x), int_round(y)
+    sigma = s * blur
+    rad = int_round(sigma * trunc)
+    v, u = np.mgrid[-rad:rad + 1, -rad:rad + 1]
+    X, Y = rx + u, ry + v
+    ok = (X >= 0) & (X < w) & (Y >= 0) & (Y < h)
+    X, Y, u, v = X[ok], Y[ok], u[ok], v[ok]
+    o = ori[Y, X]
+    o = np.where(o < 0, o + 2 * np.pi, o)
+    b = np.floor(o / (2 * np.pi) * n).astype(int) % n
+    wgt = np.exp(-(u * u + v * v) / (2 * sigma * sigma)) * mag[Y, X]
+    return np.bincount(b, weights=wgt, minlength=n)
+
+
+def sift_descriptor64(mag, ori, x, y, s, theta, N=4, Ob=8, lam=3.0, max_bin=0.2):
+    h, w = mag.shape
+    l = lam * s
+    r = np.sqrt(2.0) * l * (N + 1) / 2
+    T = np.array([[np.cos(theta), np.sin(theta)], [-np.sin(theta), np.cos(theta)]]) / l
+    rr, rx, ry = int_round(r), int_round(x), int_round(y)
+    v, u = np.mgrid[-rr:rr + 1, -rr:rr + 1]
+    X, Y = rx + u, ry + v
+    ok = (X >= 0) & (X < w) & (Y >= 0) & (Y < h)
+    X, Y, u, v = X[ok], Y[ok], u[ok], v[ok]
+    px = T[0, 0] * u + T[0, 1] * v
+    py = T[1, 0] * u + T[1, 1] * v
+    weight = np.exp(-(px * px + py * py) / (2.0 * (N * N * 0.25)))
+    m = mag[Y, X]
+    o = ori[Y, X] - theta
+    o = np.where(o < 0, o + 2 * np.pi, o) * Ob / (2 * np.pi)
+    px = px + (N / 2.0 - 0.5)
+    py = py + (N / 2.0 - 0.5)
+    keep = (np.minimum(px, py) > -1.0) & (np.maximum(px, py) < N)
+    px, py, o, weight, m = px[keep], py[keep], o[keep], weight[keep], m[keep]
+    # std::modf: integer part truncated toward zero, fraction with the sign of the argument
+    xi, yi, oi = np.trunc(px), np.trunc(py), np.trunc(o)
+    xf, yf, of = px - xi, py - yi, o - oi
+    xi, yi, oi = xi.astype(int), yi.astype(int), oi.astype(int)
+    hist = np.zeros(N * N * Ob)
+    for dy in (0, 1):
+        yy = yi + dy
+        wy = 1 - yf if dy == 0 else yf
+        for dx in (0, 1):
+            xx = xi + dx
+            wx = 1 - xf if dx == 0 else xf
+            inside = (yy >= 0) & (yy < N) & (xx >= 0) & (xx < N)
+            for do in (0, 1):
+                oo = (oi + do) % Ob
+                wo = 1 - of if do == 0 else of
+                idx = N * Ob * yy + xx * Ob + oo
+                np.add.at(hist, idx[inside], (wy * wx * wo * weight * m)[inside])
+    nrm = np.linalg.norm(hist)
+    hist = hist / nrm
+    hist = np.minimum(hist, max_bin)
+    hist = hist / np.linalg.norm(hist)
+    return np.minimum(hist * 512.0, 255.0)
+
+
+def _frame():
+    return S.tex(320, 240, 4242)
+
+
+def test_gradient_polar_against_float64():
+    img = _frame()
+    g = O.gradient_polar(img)
+    mag, ori = gradient_polar64(img)
+    assert np.allclose(g[..., 0], mag, rtol=2e-5, atol=1e-7)
+    # the angle of a (numerically) zero gradient is arbitrary
+    strong = mag > 1e-4
+    d = np.abs(g[..., 1][strong] - ori[strong])
+    d = np.minimum(d, 2 * np.pi - d)
+    assert d.max() < 1e-4
+
+
+def test_orientation_histogram_against_float64():
+    img = _frame()
+    g = O.gradient_polar(img)
+    mag, ori = g[..., 0].astype(np.float64), g[..., 1].astype(np.float64)  # same inputs for both
+    rng = np.random.default_rng(5)
+    for _ in range(40):
+        x, y = rng.uniform(-3, 323), rng.uniform(-3, 243)  # windows that leave the image included
+        s = rng.uniform(0.8, 6.0)
+        got = O.orientation_histogram(g, x, y, s)
+        want = orientation_histogram64(mag, ori, x, y, s)
+        assert np.allclose(got, want, rtol=1e-4, atol=1e-5 * max(want.max(), 1e-6)), (x, y, s)
+
+
+def test_sift_descriptor_against_float64():
+    img = _frame()
+    g = O.gradient_polar(img)
+    mag, ori = g[..., 0].astype(np.float64), g[..., 1].astype(np.float64)
+    rng = np.random.default_rng(6)
+    worst = []
+    for i in range(200):
+        x, y = rng.uniform(-2, 322), rng.uniform(-2, 242)
+        s = rng.uniform(0.6, 5.0)  # includes windows narrower than a warp and windows larger than the frame
+        # ComputeDominantOrientations hands out angles in [-pi, pi) (Orientation.cpp:110-114); outside that range
+        # "ori - theta + 2 pi" can stay negative and the reference's "% O" then indexes a neighbouring bin.
+        theta = rng.uniform(-np.pi, np.pi) if i % 5 else 0.0  # the upright form too
+        got = O.sift_descriptor(g, x, y, s, theta).astype(np.float64)
+        want = sift_descriptor64(mag, ori, x, y, s, theta)
+        assert got.shape == want.shape == (128,)
+        worst.append(np.linalg.norm(got - want) / (1e-3 * np.linalg.norm(want) + 0.05))
+    worst = np.array(worst)
+    # Unit: the parity tolerance of tests/parity.py (1e-3 |d| + 0.05 on the 0-255 scale).  Measured: every one of
+    # the descriptors within 4e-4 of that unit; a boundary sample flipping (float32 against float64) would show
+    # as a few tenths, a wrong bin index or weight as tens to hundreds.
+    assert np.mean(worst <= 0.01) >= 0.97 and worst.max() < 1.0, np.sort(worst)[-5:]
+
+
+def test_unnormalised_descriptor_against_float64():
+    """Without normalize(): the raw trilinear histogram, bin for bin (pins at(y, x, o) = N O y + O x + o)."""
+    img = _frame()
+    g = O.gradient_polar(img)
+    mag, ori = g[..., 0].astype(np.float64), g[..., 1].astype(np.float64)
+
+    x, y, s, theta = 160.3, 120.7, 2.0, 0.7
+    got = O.sift_descriptor(g, x, y, s, theta, normalize=False).astype(np.float64)
+    # the normalised float64 descriptor must be the normalisation of the oracle's raw histogram
+    h = got / np.linalg.norm(got)
+    h = np.minimum(h, 0.2)
+    h = np.minimum(h / np.linalg.norm(h) * 512.0, 255.0)
+    want = sift_descriptor64(mag, ori, x, y, s, theta)
+    assert np.linalg.norm(h - want) <= 1e-3 * np.linalg.norm(want) + 0.05
+    assert np.argmax(got) == np.argmax(want) or want[np.argmax(got)] >= 0.99 * want.max()
