@@ -162,3 +162,66 @@ def test_unnormalised_descriptor_against_float64():
     want = sift_descriptor64(mag, ori, x, y, s, theta)
     assert np.linalg.norm(h - want) <= 1e-3 * np.linalg.norm(want) + 0.05
     assert np.argmax(got) == np.argmax(want) or want[np.argmax(got)] >= 0.99 * want.max()
+
+
+# ---- the Gaussian / DoG pyramid ------------------------------------------------------------------------------------
+#   make_gaussian_kernel, apply_row/column_based_filter     ImageProcessing/LinearFiltering.hpp:78-149, 172-203
+#   gaussian_pyramid (first octave 0), downscale            ImageProcessing/GaussianPyramid.hpp:36-123, Resize.cpp:31-83
+#   difference_of_gaussians_pyramid                         ImageProcessing/GaussianPyramid.cpp:23-51
+def _kernel64(sigma32, truncate=4.0):
+    size = int(np.float32(2) * np.float32(truncate) * sigma32 + np.float32(1))  # the reference sizes it in float
+    size = max(3, size)
+    size += 1 - size % 2
+    c = size // 2
+    k = np.exp(-(np.arange(size, dtype=np.float64) - c) ** 2 / (2.0 * float(sigma32) ** 2))
+    return k / k.sum()
+
+
+def _gaussian64(img, sigma32):
+    from scipy.ndimage import correlate1d
+
+    k = _kernel64(sigma32)
+    rows = correlate1d(img, k, axis=1, mode="nearest")  # x first, borders replicated
+    return correlate1d(rows, k, axis=0, mode="nearest")
+
+
+def _pyramid64(img, scale_camera=0.5, scale_initial=1.6, scales_per_octave=3 + 3, pad=1, max_octaves=100):
+    f32 = np.float32
+    I = img.astype(np.float64)
+    cam, init = f32(scale_camera), f32(scale_initial)
+    if cam < init:
+        I = _gaussian64(I, np.sqrt(init * init - cam * cam, dtype=f32))
+    h, w = I.shape
+    n_oct = min(int(np.log(f32(min(w, h)) / (f32(2) * f32(pad))) / np.log(f32(2))), max_octaves)
+    k = np.power(f32(2), f32(1) / f32(3), dtype=f32)  # std::pow(2.f, 1.f / 3.f)
+    down = int(np.floor(np.log(f32(2)) / np.log(k)))
+    G = []
+    for o in range(n_oct):
+        if o > 0:
+            src = G[o - 1][down]
+            sh, sw = src.shape
+            dh, dw = sh // 2, sw // 2
+            ys = (np.arange(dh) * (f32(sh) / f32(dh))).astype(int)  # nearest sample at float ratio, truncated
+            xs = (np.arange(dw) * (f32(sw) / f32(dw))).astype(int)
+            I = src[np.ix_(ys, xs)]
+        layers, sig = [I], init
+        for s in range(1, scales_per_octave):
+            ks = k * sig
+            layers.append(_gaussian64(layers[-1], np.sqrt(ks * ks - sig * sig, dtype=f32)))
+            sig = f32(sig * k)
+        G.append(layers)
+    return G
+
+
+def test_gaussian_and_dog_pyramid_against_float64():
+    img = S.tex(322, 241, 99)  # odd sizes: the even sub-sampling of every octave drops a row / column
+    ref = O.compute_sift_keypoints(img, O.PyramidParams(first_octave_index=0), parallel=True)
+    G = _pyramid64(img)
+    assert ref.num_octaves == len(G) and ref.num_scales == len(G[0]) == 6
+    for o in range(len(G)):
+        for s in range(6):
+            got = ref.gaussian(s, o)
+            assert got.shape == G[o][s].shape, (s, o)
+            assert np.abs(got - G[o][s]).max() < 2e-6, (s, o)  # fp32 sums of <= 25 products of values in [0, 1]
+            if s < 5:
+                assert np.abs(ref.dog(s, o) - (G[o][s + 1] - G[o][s])).max() < 3e-6, (s, o)
