@@ -393,3 +393,41 @@ def test_dominant_orientations_against_float64():
     diffs = np.array(diffs)
     # measured: 412 angles, 411 within 1e-5 rad, one flat peak (tiny second difference) at 4.6e-4
     assert np.mean(diffs < 1e-4) >= 0.99 and diffs.max() < 2e-3, np.sort(diffs)[-5:]
+
+
+# ---- the wiring of compute_sift_keypoints ----------------------------------------------------------------------------
+#   FeatureDetectors/SIFT.cpp:27-108; ComputeDominantOrientations on the pyramid, Orientation.cpp:120-166;
+#   ComputeSIFTDescriptor on the keypoint list, FeatureDescriptors/SIFT.hpp:150-200
+def test_whole_chain_wiring_against_float64():
+    """Which layer feeds the gradients (the Gaussian G(s, o) of the extremum's own (s, o)), which scale goes where
+    (the orientation window uses the layer's nominal scale, the descriptor the REFINED one), one keypoint per
+    dominant orientation in extremum order, and the final rescaling to image coordinates."""
+    img = S.tex(480, 360, 21)
+    ref = O.compute_sift_keypoints(img, O.PyramidParams(first_octave_index=0), parallel=True)
+    ext, kps, desc = ref.extrema, ref.keypoints, ref.descriptors
+    assert len(ext) > 150 and len(kps) >= len(ext)
+    k32 = np.power(np.float32(2), np.float32(1) / np.float32(3), dtype=np.float32)
+    polar = {}
+    j, n_desc_ok = 0, 0
+    for e in ext:
+        s, o = int(e["s"]), int(e["o"])
+        if (s, o) not in polar:
+            polar[(s, o)] = gradient_polar64(ref.gaussian(s, o))
+        mag, ori = polar[(s, o)]
+        nominal = float(np.float32(k32 ** np.float32(s)) * np.float32(1.6))
+        thetas, _ = dominant_orientations64(mag, ori, float(e["x"]), float(e["y"]), nominal)
+        refined = 1.0 / np.sqrt(float(e["shape"][0]))
+        z = float(ref.octave_scaling(o))
+        for th in thetas:
+            kp = kps[j]
+            assert (int(kp["s"]), int(kp["o"]), int(kp["xi"]), int(kp["yi"])) == (s, o, int(e["xi"]), int(e["yi"])), j
+            d = abs(float(kp["orientation"]) - th)
+            assert min(d, 2 * np.pi - d) < 2e-3, (j, kp["orientation"], th)
+            assert abs(kp["x"] - e["x"] * z) < 1e-3 * z and abs(kp["y"] - e["y"] * z) < 1e-3 * z
+            assert abs(kp["shape"][0] - e["shape"][0] / (z * z)) < 1e-5 * e["shape"][0] / (z * z)
+            want = sift_descriptor64(mag, ori, float(e["x"]), float(e["y"]), refined, float(kp["orientation"]))
+            err = np.linalg.norm(desc[j] - want) / (1e-3 * np.linalg.norm(want) + 0.05)
+            n_desc_ok += err <= 1.0
+            j += 1
+    assert j == len(kps), (j, len(kps))  # same number of orientations for every extremum
+    assert n_desc_ok >= 0.995 * len(kps), (n_desc_ok, len(kps))
