@@ -185,11 +185,31 @@ def _gaussian64(img, sigma32):
     return correlate1d(rows, k, axis=0, mode="nearest")
 
 
-def _pyramid64(img, scale_camera=0.5, scale_initial=1.6, scales_per_octave=3 + 3, pad=1, max_octaves=100):
+def _enlarge64(img, fact):
+    """enlarge + interpolate (Resize.cpp:86-128, Interpolation.hpp:34-78): bilinear at dst * (src / dst), the
+    neighbour past the last row / column replaced by the last one; the result is stored as float."""
+    h, w = img.shape
+    dh, dw = int(h * fact), int(w * fact)
+    py, px = np.arange(dh) * (h / dh), np.arange(dw) * (w / dw)
+    y0, x0 = np.floor(py).astype(int), np.floor(px).astype(int)
+    fy, fx = (py - y0)[:, None], (px - x0)[None, :]
+    y1, x1 = np.minimum(y0 + 1, h - 1), np.minimum(x0 + 1, w - 1)
+    f = img.astype(np.float64)
+    out = (1 - fy) * (1 - fx) * f[np.ix_(y0, x0)] + (1 - fy) * fx * f[np.ix_(y0, x1)] + \
+        fy * (1 - fx) * f[np.ix_(y1, x0)] + fy * fx * f[np.ix_(y1, x1)]
+    return out.astype(np.float32).astype(np.float64)
+
+
+def _pyramid64(img, first_octave=0, scale_camera=0.5, scale_initial=1.6, scales_per_octave=3 + 3, pad=1,
+               max_octaves=100):
     f32 = np.float32
     I = img.astype(np.float64)
-    cam, init = f32(scale_camera), f32(scale_initial)
-    if cam < init:
+    resize = f32(2.0) ** f32(-first_octave)
+    cam, init = f32(scale_camera) * resize, f32(scale_initial)
+    if first_octave < 0:
+        I = _enlarge64(img, float(resize))  # and NO blur up to scale_initial: GaussianPyramid.hpp:55-56
+    elif cam < init:
+        assert first_octave == 0
         I = _gaussian64(I, np.sqrt(init * init - cam * cam, dtype=f32))
     h, w = I.shape
     n_oct = min(int(np.log(f32(min(w, h)) / (f32(2) * f32(pad))) / np.log(f32(2))), max_octaves)
@@ -213,10 +233,15 @@ def _pyramid64(img, scale_camera=0.5, scale_initial=1.6, scales_per_octave=3 + 3
     return G
 
 
-def test_gaussian_and_dog_pyramid_against_float64():
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("first_octave", [0, -1])
+def test_gaussian_and_dog_pyramid_against_float64(first_octave):
     img = S.tex(322, 241, 99)  # odd sizes: the even sub-sampling of every octave drops a row / column
-    ref = O.compute_sift_keypoints(img, O.PyramidParams(first_octave_index=0), parallel=True)
-    G = _pyramid64(img)
+    ref = O.compute_sift_keypoints(img, O.PyramidParams(first_octave_index=first_octave), parallel=True)
+    G = _pyramid64(img, first_octave)
+    assert ref.octave_scaling(0) == 2.0 ** first_octave
     assert ref.num_octaves == len(G) and ref.num_scales == len(G[0]) == 6
     for o in range(len(G)):
         for s in range(6):
