@@ -11,7 +11,12 @@
 // HDF5 are hard requirements and absent), so this is a "port" oracle.  It is
 // pinned against the reference's own known-answer tests (tests/test_oracle_*.py
 // port them one by one); the reference holds NO golden keypoints/descriptors, so
-// the end-to-end output of compute_sift_keypoints is **parity unpinned**.
+// the end-to-end output of compute_sift_keypoints is **parity unpinned** by the
+// reference binary.  What stands in for it: tests/test_independent_float64_pin.py,
+// a second implementation of every stage (pyramid, extrema, orientations,
+// descriptors, the wiring of the chain) in float64 numpy written from the
+// reference sources, not from this file, and tests/test_eigen_boundary_pin.py
+// (float64 LAPACK against the restated Eigen routines).
 //
 // Every function cites the reference file:line it restates (paths relative to
 // /root/reference/cpp/src/DO/Sara/).  Deliberately reproduced reference quirks
