@@ -456,3 +456,26 @@ def test_whole_chain_wiring_against_float64():
             j += 1
     assert j == len(kps), (j, len(kps))  # same number of orientations for every extremum
     assert n_desc_ok >= 0.995 * len(kps), (n_desc_ok, len(kps))
+
+
+# ---- function pyramids of the sibling detectors ------------------------------------------------------------------------
+#   laplacian_pyramid (scale-normalised)        ImageProcessing/GaussianPyramid.hpp:153-178, Differential.hpp:106-135
+#   det_of_hessian_pyramid                      FeatureDetectors/Hessian.hpp:35-57, Differential.hpp:191-226
+@pytest.mark.parametrize("which", ["log", "doh"])
+def test_function_pyramids_against_float64(which):
+    img = S.tex(200, 150, 5)
+    res = O.compute_function_extrema(img, which, O.PyramidParams(first_octave_index=0, scale_count_per_octave=5))
+    k32 = np.power(np.float32(2), np.float32(1) / np.float32(3), dtype=np.float32)
+    assert res.num_scales == 5 and res.num_octaves >= 4
+    for o in range(res.num_octaves):
+        for s in range(res.num_scales):
+            g = np.pad(res.gaussian(s, o).astype(np.float64), 1, mode="edge")  # replicated border
+            c = g[1:-1, 1:-1]
+            hxx = g[1:-1, 2:] - 2 * c + g[1:-1, :-2]
+            hyy = g[2:, 1:-1] - 2 * c + g[:-2, 1:-1]
+            hxy = (g[2:, 2:] - g[2:, :-2] - g[:-2, 2:] + g[:-2, :-2]) / 4
+            rel = float(np.float32(k32 ** np.float32(s)) * np.float32(1.6))  # scale_relative_to_octave(s)
+            want = (hxx + hyy) * rel ** 2 if which == "log" else (hxx * hyy - hxy * hxy) * rel ** 4
+            got = res.dog(s, o)
+            assert got.shape == want.shape
+            assert np.abs(got - want).max() <= 2e-5 * max(np.abs(want).max(), 1e-3), (which, s, o)
