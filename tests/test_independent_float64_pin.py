@@ -478,4 +478,5 @@ def test_function_pyramids_against_float64(which):
             want = (hxx + hyy) * rel ** 2 if which == "log" else (hxx * hyy - hxy * hxy) * rel ** 4
             got = res.dog(s, o)
             assert got.shape == want.shape
-            assert np.abs(got - want).max() <= 2e-5 * max(np.abs(want).max(), 1e-3), (which, s, o)
+            # fp32 second differences of values in [0, 1] carry ~1e-7; the scale normalisation multiplies that
+            assert np.abs(got - want).max() <= 5e-5 * max(np.abs(want).max(), 1e-3), (which, s, o)
