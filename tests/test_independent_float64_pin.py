@@ -480,3 +480,110 @@ def test_function_pyramids_against_float64(which):
             assert got.shape == want.shape
             # fp32 second differences of values in [0, 1] carry ~1e-7; the scale normalisation multiplies that
             assert np.abs(got - want).max() <= 5e-5 * max(np.abs(want).max(), 1e-3), (which, s, o)
+
+
+# ---- Hessian-Laplace -------------------------------------------------------------------------------------------------
+#   ComputeHessianLaplaceMaxima::operator()      FeatureDetectors/Hessian.cpp:19-57
+#   laplace_maxima, select_laplace_scale          FeatureDetectors/RefineExtremum.cpp:523-709
+#   refine_extremum (2-D)                         FeatureDetectors/RefineExtremum.cpp:132-221
+#   LocalMax (non-strict, 8 neighbours)           ImageProcessing/Extrema.hpp:28-60, 106
+def _select_laplace_scale64(Gprev, x, y, rel_s, rel_prev, num_scales):
+    f32 = np.float32
+    radius = int(np.ceil(np.sqrt(f32(2)) * f32(4)))
+    h, w = Gprev.shape
+    if x - radius < 0 or x + radius >= w or y - radius < 0 or y + radius >= h:
+        return None
+    patch = Gprev[y - radius:y + radius + 1, x - radius:x + radius + 1]
+    ratio = np.power(f32(2), f32(1) / f32(num_scales), dtype=f32)
+    scales = [f32(rel_s) / np.sqrt(f32(2))]
+    with np.errstate(invalid="ignore"):
+        inc = np.sqrt(scales[0] * scales[0] - f32(rel_prev) * f32(rel_prev), dtype=f32)  # NaN: k < sqrt(2)
+    patches = [_gaussian64(patch, inc) if inc > f32(1e-3) else patch]
+    for i in range(1, num_scales + 1):
+        scales.append(f32(ratio * scales[i - 1]))
+        inc = np.sqrt(scales[i] * scales[i] - scales[i - 1] * scales[i - 1], dtype=f32)
+        patches.append(_gaussian64(patches[i - 1], inc))
+    c = radius
+    logs = [(p[c, c + 1] + p[c, c - 1] + p[c + 1, c] + p[c - 1, c] - 4 * p[c, c]) * float(s) ** 2
+            for p, s in zip(patches, scales)]
+    for i in range(1, num_scales):
+        if (logs[i] <= logs[i - 1] and logs[i] <= logs[i + 1]) or (logs[i] >= logs[i - 1] and logs[i] >= logs[i + 1]):
+            fp = (logs[i + 1] - logs[i - 1]) / 2
+            fs = logs[i - 1] - 2 * logs[i] + logs[i + 1]
+            return float(scales[i]) * float(ratio) ** (-fp / fs)
+    return None
+
+
+def _refine2d64(F, x, y, pad, n_iter):
+    """type = 1.  Returns (px, py, value)."""
+    h, w = F.shape
+    x0, y0, v0 = x, y, F[y, x]
+    hv, g = np.zeros(2), np.zeros(2)
+    for _ in range(n_iter):
+        if x < pad or x >= w - pad or y < pad or y >= h - pad:
+            break
+        g = np.array([(F[y, x + 1] - F[y, x - 1]) / 2, (F[y + 1, x] - F[y - 1, x]) / 2])
+        hxx = F[y, x + 1] - 2 * F[y, x] + F[y, x - 1]
+        hyy = F[y + 1, x] - 2 * F[y, x] + F[y - 1, x]
+        hxy = (F[y + 1, x + 1] - F[y + 1, x - 1] - F[y - 1, x + 1] + F[y - 1, x - 1]) / 4
+        if hxx * hyy - hxy * hxy <= 0 or hxx + hyy >= 0:
+            g = np.zeros(2)  # the offset of an earlier iteration, if any, stays
+            break
+        hv = -np.linalg.solve(np.array([[hxx, hxy], [hxy, hyy]]), g)
+        if np.abs(hv).max() > 1.5:
+            return float(x0), float(y0), v0  # "return false", ignored by the caller: p and val keep their initial values
+        if np.abs(hv).min() > 0.6:
+            x += 1 if hv[0] > 0 else -1
+            y += 1 if hv[1] > 0 else -1
+            continue
+        break
+    old = F[y, x]
+    new = old + 0.5 * g.dot(hv)
+    if old <= new:
+        return x + hv[0], y + hv[1], new
+    return float(x), float(y), v0
+
+
+def test_hessian_laplace_against_float64():
+    img = S.tex(320, 240, 13)
+    pp = O.PyramidParams(first_octave_index=0, scale_count_per_octave=4)
+    pad, num_scales, iters, thres = 1, 10, 5, float(np.float32(1e-5))
+    ref = O.compute_hessian_laplace(img, pp, 1e-5, pad, num_scales, iters)
+    got = ref.extrema
+    k32 = np.power(np.float32(2), np.float32(1) / np.float32(3), dtype=np.float32)
+    rel = lambda s: float(np.float32(k32 ** np.float32(s)) * np.float32(1.6))
+    want = []
+    for o in range(ref.num_octaves):
+        G = [ref.gaussian(s, o).astype(np.float64) for s in range(ref.num_scales)]
+        for s in range(1, ref.num_scales):
+            F = ref.dog(s, o).astype(np.float64)  # the det-of-Hessian layer (pinned above)
+            h, w = F.shape
+            for y in range(pad, h - pad):
+                for x in range(pad, w - pad):
+                    v = F[y, x]
+                    if v < thres:
+                        continue
+                    nb = F[y - 1:y + 2, x - 1:x + 2]
+                    if (nb > v).any():
+                        continue
+                    scale = _select_laplace_scale64(G[s - 1], x, y, rel(s), rel(s - 1), num_scales)
+                    if scale is None:
+                        continue
+                    px, py, val = _refine2d64(F, x, y, pad, iters)
+                    want.append((o, x, y, s, px, py, scale, val))
+    assert len(got) > 100, len(got)
+    key_got = [(int(e["o"]), int(e["xi"]), int(e["yi"]), int(e["s"])) for e in got]
+    key_want = [w_[:4] for w_ in want]
+    common = set(key_got) & set(key_want)
+    assert len(common) >= 0.99 * max(len(key_got), len(key_want)), (len(key_got), len(key_want), len(common))
+    assert [k for k in key_got if k in common] == [k for k in key_want if k in common]
+    idx = {k: i for i, k in enumerate(key_want)}
+    n_ok = 0
+    for e, k in zip(got, key_got):
+        if k not in common:
+            continue
+        w_ = want[idx[k]]
+        scale = 1.0 / np.sqrt(float(e["shape"][0]))
+        n_ok += abs(e["x"] - w_[4]) < 1e-3 and abs(e["y"] - w_[5]) < 1e-3 and abs(scale - w_[6]) < 1e-3 * w_[6] and \
+            abs(e["extremum_value"] - w_[7]) <= 1e-4 * abs(w_[7]) + 1e-9
+    assert n_ok >= 0.98 * len(common), (n_ok, len(common))
