@@ -587,3 +587,32 @@ def test_hessian_laplace_against_float64():
         n_ok += abs(e["x"] - w_[4]) < 1e-3 and abs(e["y"] - w_[5]) < 1e-3 and abs(scale - w_[6]) < 1e-3 * w_[6] and \
             abs(e["extremum_value"] - w_[7]) <= 1e-4 * abs(w_[7]) + 1e-9
     assert n_ok >= 0.98 * len(common), (n_ok, len(common))
+
+
+# ---- Harris-Laplace: the cornerness layers (laplace_maxima itself is pinned by the Hessian-Laplace test) ---------------
+#   ComputeHarrisLaplaceCorners::operator()      FeatureDetectors/Harris.cpp:165-230
+def test_harris_cornerness_against_float64():
+    img = S.tex(200, 150, 17)
+    k = float(np.sqrt(np.float32(2.0)))
+    ref = O.compute_harris_laplace(img, O.PyramidParams(0, 3, k, 1), kappa=0.04)
+    assert ref.num_scales == 3 and ref.num_octaves >= 4
+    kf = np.float32(k)
+    for o in range(ref.num_octaves):
+        for s in range(ref.num_scales):
+            g = ref.gaussian(s, o).astype(np.float64)
+            gx = np.empty_like(g)
+            gy = np.empty_like(g)
+            gx[:, 1:-1] = (g[:, 2:] - g[:, :-2]) / 2
+            gx[:, 0] = (g[:, 1] - g[:, 0]) / 2
+            gx[:, -1] = (g[:, -1] - g[:, -2]) / 2
+            gy[1:-1, :] = (g[2:, :] - g[:-2, :]) / 2
+            gy[0, :] = (g[1, :] - g[0, :]) / 2
+            gy[-1, :] = (g[-1, :] - g[-2, :]) / 2
+            sigma_i = np.float32(kf ** np.float32(s)) * np.float32(1.6)
+            sigma_d = float(sigma_i * (np.float32(1) / np.sqrt(np.float32(2))))
+            a, b, c = (_gaussian64(m, sigma_i) for m in (gx * gx, gx * gy, gy * gy))
+            want = ((a * c - b * b) - 0.04 * (a + c) ** 2) * sigma_d ** 2
+            got = ref.dog(s, o)
+            assert got.shape == want.shape
+            # products of small gradients: the layer is of the order 1e-6 .. 1e-4
+            assert np.abs(got - want).max() <= 2e-4 * np.abs(want).max() + 1e-12, (s, o, np.abs(want).max())
