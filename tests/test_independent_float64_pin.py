@@ -423,14 +423,16 @@ def test_dominant_orientations_against_float64():
 # ---- the wiring of compute_sift_keypoints ----------------------------------------------------------------------------
 #   FeatureDetectors/SIFT.cpp:27-108; ComputeDominantOrientations on the pyramid, Orientation.cpp:120-166;
 #   ComputeSIFTDescriptor on the keypoint list, FeatureDescriptors/SIFT.hpp:150-200
-def test_whole_chain_wiring_against_float64():
+@pytest.mark.parametrize("first_octave", [0, -1])
+def test_whole_chain_wiring_against_float64(first_octave):
     """Which layer feeds the gradients (the Gaussian G(s, o) of the extremum's own (s, o)), which scale goes where
     (the orientation window uses the layer's nominal scale, the descriptor the REFINED one), one keypoint per
     dominant orientation in extremum order, and the final rescaling to image coordinates."""
-    img = S.tex(480, 360, 21)
-    ref = O.compute_sift_keypoints(img, O.PyramidParams(first_octave_index=0), parallel=True)
+    img = S.tex(480, 360, 21) if first_octave == 0 else S.tex(300, 220, 22)
+    ref = O.compute_sift_keypoints(img, O.PyramidParams(first_octave_index=first_octave), parallel=True)
+    assert ref.octave_scaling(0) == 2.0 ** first_octave  # positions of octave 0 are halved when the frame was doubled
     ext, kps, desc = ref.extrema, ref.keypoints, ref.descriptors
-    assert len(ext) > 150 and len(kps) >= len(ext)
+    assert len(ext) > 80 and len(kps) >= len(ext)
     k32 = np.power(np.float32(2), np.float32(1) / np.float32(3), dtype=np.float32)
     polar = {}
     j, n_desc_ok = 0, 0
